@@ -1,0 +1,359 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the DOODLE flux-renderer hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+One "step" = one ``HelioEnv.step(action)`` (noisy render forward, target render, the four losses)
+followed by ``(mse + dist + bound + alignment_loss).backward()`` down to ``action.grad`` on the
+BASELINE.json headline configuration: N=2000 heliostats, 256x256 receiver, B=4096 suns per GPU
+(weak scaling: the sun batch is sharded, heliostat geometry replicated, one 4-float all-reduce per
+step).  ``value`` = heliostat*pixel evals/s = (B_global * N * R^2) / step time, inputs resident in
+HBM; ``e2e`` = the same with the action in pinned host memory (H2D inside the timed region) and the
+action gradient + metrics read back (D2H).
+
+``--impl reference`` times the oracle port of the reference's CPU algorithm (oracle/helio_oracle.py,
+numpy, all host threads) on a bounded sample of the same workload; the reference itself is pure
+Python that cannot travel to the GPU box.  One JSON line on stdout either way.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = dict(name="large_field N=2000 R=256 B=4096/GPU (BASELINE.json configs[3])", N=2000, R=256, B=4096,
+                sigma_scale=0.01, error_scale_mrad=90.0)
+METRIC = "heliostat_pixel_evals_per_s (HelioEnv.step fwd + losses + backward to action.grad)"
+UNIT = "evals/s"
+FLOP_PER_EVAL = {"splat_fwd": 2.0, "splat_bwd": 4.0}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--N", type=int, default=WORKLOAD["N"])
+    ap.add_argument("--R", type=int, default=WORKLOAD["R"])
+    ap.add_argument("--B", type=int, default=WORKLOAD["B"], help="suns per GPU")
+    ap.add_argument("--splat", default="auto", choices=["auto", "simt", "tc"])
+    ap.add_argument("--cache-target", action="store_true", help="cache the target render (exact; off = reference-faithful)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget for the cpu_baseline sample")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------
+# synthetic workload: identical on CPU and GPU
+# ---------------------------------------------------------------------------------------------
+def make_inputs(N, B, seed=42, rank=0):
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    helio = torch.rand(N, 3, generator=g) * 10 + 80          # train_with_env.py:227
+    helio[:, 2] = 0
+    targ_pos = torch.tensor([0., -5., 0.])
+    targ_norm = torch.tensor([0., 1., 0.])
+    area = (15., 15.)
+    g2 = torch.Generator().manual_seed(seed + 1 + rank)
+    return helio, targ_pos, targ_norm, area, g2
+
+
+def sample_suns(B, gen):
+    """B directions in a 2-degree cone about az=el=45 deg, |z|, radius hypot(1e4,1e4) (test_environment.py:42-88,293,324)."""
+    import torch
+    from doodle_b200.env import azimuth_elevation_to_primary_direction
+    import torch.nn.functional as F
+    a = azimuth_elevation_to_primary_direction(45.0, 45.0)
+    alpha = math.radians(2.0)
+    helper = torch.tensor([0., 0., 1.])
+    u = F.normalize(torch.linalg.cross(helper, a), dim=0)
+    v = torch.linalg.cross(a, u)
+    ct = 1.0 - torch.rand(B, generator=gen) * (1.0 - math.cos(alpha))
+    st = torch.sqrt(torch.clamp(1.0 - ct ** 2, min=0.0))
+    phi = 2.0 * math.pi * torch.rand(B, generator=gen)
+    d = u[None] * (st * torch.cos(phi))[:, None] + v[None] * (st * torch.sin(phi))[:, None] + a[None] * ct[:, None]
+    d = F.normalize(d, dim=1)
+    d[:, 2] = d[:, 2].abs()
+    return d * math.hypot(10000, 10000)
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm: oracle port of the reference algorithm
+# ---------------------------------------------------------------------------------------------
+def cpu_step_factory(N, R, n_suns, threads):
+    import numpy as np
+    import torch
+    from oracle import helio_oracle as orc
+    helio, targ_pos, targ_norm, area, gen = make_inputs(N, n_suns)
+    sun = sample_suns(n_suns, gen).numpy()
+    helio_n = helio.numpy()
+    ideal = orc.calculate_ideal_normals(sun, helio_n, targ_pos.numpy())
+    act = ideal + 0.01 * torch.randn(ideal.shape, generator=gen).numpy()
+    act = (act / np.linalg.norm(act, axis=2, keepdims=True)).astype(np.float32)
+    errs = (torch.randn(n_suns, N, 2, generator=gen) * WORKLOAD["error_scale_mrad"]).numpy()
+    dmaps = torch.rand(n_suns, R, R, generator=gen).numpy() * 50
+
+    def step():
+        return orc.env_step(sun, act, errs, helio_n, targ_pos.numpy(), targ_norm.numpy(), area, R,
+                            WORKLOAD["sigma_scale"], dmaps, threads=threads)
+    return step
+
+
+def run_cpu_sample(N, R, budget_s, steps=1, warmup=0):
+    """Time the oracle port on a bounded sample; returns dict for `cpu_baseline`."""
+    threads = os.cpu_count() or 1
+    # calibrate on one sun per thread-group of 1 to pick the sample size
+    t0 = time.perf_counter()
+    cpu_step_factory(N, R, 1, 1)()
+    t_one = time.perf_counter() - t0
+    per_step_budget = max(budget_s / max(steps + warmup, 1), t_one)
+    n_suns = int(max(1, min(threads * 4, threads * per_step_budget / max(t_one, 1e-6))))
+    n_suns = max(1, min(n_suns, 4 * threads))
+    step = cpu_step_factory(N, R, n_suns, threads)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(max(steps, 1)):
+        step()
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    evals = float(n_suns) * N * R * R
+    return dict(value=evals / dt, unit=UNIT, cores=threads, kind="port",
+                sample=f"oracle/helio_oracle.env_step (numpy port of the reference's dense algorithm, fp32): "
+                       f"{n_suns} suns x N={N} x R={R}, step fwd+target+losses+bwd, {dt:.2f} s/step on {threads} threads"), dt
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    steps, warmup = max(args.steps, 1), max(args.warmup, 0)
+    cb, dt = run_cpu_sample(args.N, args.R, budget_s=150.0, steps=steps, warmup=warmup)
+    line = dict(impl="reference", metric=METRIC, value=cb["value"], unit=UNIT, n_gpus=args.gpus, steps=steps, warmup=warmup,
+                ms_per_step=dt * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                config=dict(workload=WORKLOAD["name"], N=args.N, R=args.R, B_per_gpu=args.B, note="bounded sample, see cpu_baseline.sample"),
+                cpu_baseline=cb,
+                e2e=dict(value=cb["value"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line))
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                       "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons, power = [], [], set(), []
+        for ln in self.f.read().strip().splitlines():
+            c = [x.strip() for x in ln.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2])); power.append(float(c[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            sm.sort()
+            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm),
+                       power_w_max=max(power))
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        return out
+
+
+def measure_tf32_peak(torch):
+    """cuBLAS TF32 GEMM burst rate on this box (denominator of the 3xTF32 roofline = this / 3)."""
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        n = 8192
+        a = torch.randn(n, n, device="cuda"); b = torch.randn(n, n, device="cuda")
+        for _ in range(3):
+            a @ b
+        best = float("inf")
+        for _ in range(8):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); a @ b; e1.record(); torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+
+
+def main_ours(args):
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a B200; doodle_b200 has no CPU fallback")
+    from doodle_b200 import HelioEnv, functional as Fn, _lib
+    from doodle_b200.dist import make_sharded_env
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+
+    N, R, B = args.N, args.R, args.B
+    helio, targ_pos, targ_norm, area, gen = make_inputs(N, B, rank=rank)
+    torch.manual_seed(42 + rank)
+    kw = dict(heliostat_pos=helio.to(dev), targ_pos=targ_pos.to(dev), targ_area=area, targ_norm=targ_norm.to(dev),
+              sigma_scale=WORKLOAD["sigma_scale"], error_scale_mrad=WORKLOAD["error_scale_mrad"], initial_action_noise=0.0,
+              resolution=R, device=str(dev), new_errors_every_reset=True, cache_target=args.cache_target, check_finite=False)
+    if world > 1:
+        env = make_sharded_env(HelioEnv, global_batch_size=B * world, **kw)
+    else:
+        env = HelioEnv(batch_size=B, **kw)
+    impl = dict(auto=_lib.SPLAT_AUTO, simt=_lib.SPLAT_SIMT, tc=_lib.SPLAT_TC)[args.splat]
+    env.noisy_field.splat_impl = impl
+    env.ref_field.splat_impl = impl
+    env.reset()
+    action0 = env.noisy_field.initial_action.detach().clone().view(B, N, 3)
+    action0 = action0 + 0.01 * torch.randn_like(action0)
+    action0 = (action0 / action0.norm(dim=2, keepdim=True)).contiguous()
+
+    def one_step(action):
+        action = action.detach().requires_grad_(True)
+        obs, metrics, monitor = env.step(action)
+        loss = metrics["mse"] + metrics["dist"] + metrics["bound"] + metrics["alignment_loss"]
+        loss.backward()
+        return action.grad, metrics
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    steps, warmup = max(args.steps, 1), max(args.warmup, 3)
+    # ---- device-resident arm --------------------------------------------------------------
+    for _ in range(warmup):
+        one_step(action0)
+    Fn.reset_profile(True)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    launches0 = Fn.launch_count()
+    ms_total = timed(lambda: one_step(action0), steps)
+    launches = Fn.launch_count() - launches0
+    clocks = sampler.stop() if sampler else None
+    kprof = Fn.collect_profile()
+    Fn.reset_profile(False)
+    ms_step = ms_total / steps
+    evals_step = float(B) * world * N * R * R
+
+    # ---- end-to-end arm: host action in, host gradient + metrics out ------------------------
+    h_action = action0.cpu().pin_memory()
+    h_grad = torch.empty_like(h_action).pin_memory()
+    h_metrics = torch.empty(4, dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        a = h_action.to(dev, non_blocking=True)
+        g, m = one_step(a)
+        h_grad.copy_(g, non_blocking=True)
+        h_metrics.copy_(torch.stack([m["mse"], m["dist"], m["bound"], m["alignment_loss"]]).detach(), non_blocking=True)
+        torch.cuda.current_stream().synchronize()      # the caller reads the result every step
+
+    for _ in range(2):
+        e2e_step()
+    ms_e2e = timed(e2e_step, steps) / steps
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel ------------------------------------------------------
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    tf32 = measure_tf32_peak(torch)
+    dom = max(("splat_fwd", "splat_bwd"), key=lambda k: kprof.get(k, {}).get("total_ms", 0.0))
+    d = kprof.get(dom, {})
+    avg_ms = d.get("avg_ms") or float("nan")
+    flops_launch = FLOP_PER_EVAL[dom] * float(B) * N * R * R
+    achieved = flops_launch / (avg_ms * 1e-3) / 1e12
+    peak = tf32 / 3.0
+    roofline = dict(bound="tensor", kernel=dom, achieved=achieved, peak=peak, unit="TFLOP/s", frac=achieved / peak, traffic=None,
+                    avg_launch_ms=avg_ms, share_of_step=d.get("total_ms", 0.0) / ms_total if ms_total else None,
+                    note=f"algorithmic {FLOP_PER_EVAL[dom]:.0f} FLOP/eval x {B*N*R*R:.3e} evals per launch; peak = cuBLAS TF32 "
+                         f"{tf32:.0f} TFLOP/s measured in this run / 3 (3xTF32 for fp32 accuracy); bf16 peak of measured "
+                         f"{peaks.get('bf16_tflops', 'n/a')} for context; per-kernel ms over the timed region: "
+                         + ", ".join(f"{k}={v['avg_ms']:.3f}x{v['n']}" for k, v in sorted(kprof.items())))
+
+    cpu_baseline = None
+    if not args.no_cpu_baseline:
+        cpu_baseline, _ = run_cpu_sample(N, R, budget_s=args.cpu_seconds)
+
+    line = dict(metric=METRIC, value=evals_step / (ms_step * 1e-3), unit=UNIT, n_gpus=world, steps=steps, warmup=warmup,
+                ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                env_steps_per_s=1e3 / ms_step,
+                config=dict(workload=WORKLOAD["name"], N=N, R=R, B_per_gpu=B, global_batch=B * world, parallelism=f"dp{world}",
+                            splat=args.splat, target_cached=bool(args.cache_target), l2="inputs larger than L2 (4 GB of images per step)",
+                            renders_per_step="noisy fwd+bwd, target fwd" if not args.cache_target else "noisy fwd+bwd"),
+                clocks=clocks,
+                e2e=dict(value=evals_step / (ms_e2e * 1e-3), unit=UNIT, ms_per_step=ms_e2e,
+                         h2d_bytes_per_step=h_action.numel() * 4, d2h_bytes_per_step=h_grad.numel() * 4 + 16),
+                gpu_launches=launches, roofline=roofline, cpu_baseline=cpu_baseline)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    a = parse()
+    sys.exit(main_reference(a) if a.impl == "reference" else main_ours(a))

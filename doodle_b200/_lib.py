@@ -1,0 +1,110 @@
+"""ctypes binding of libhelio_sm100.so (the C ABI declared in include/helio_b200.h).
+
+There is no CPU fallback: if the shared library is missing or the device is not a cc-10.x GPU the
+product path raises.  ``build()`` compiles the library in-tree with nvcc (sm_100a only).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libhelio_sm100.so")
+CSRC = os.path.join(_HERE, "csrc")
+ABI_VERSION = 1
+
+SPLAT_AUTO, SPLAT_SIMT, SPLAT_TC = 0, 1, 2
+
+EXPORTS = (
+    "helio_abi_version", "helio_last_error", "helio_device_ok", "helio_geom_workspace_bytes", "helio_geom_fwd",
+    "helio_geom_bwd", "helio_splat_fwd", "helio_splat_bwd", "helio_image_max", "helio_loss_fwd", "helio_loss_bwd",
+)
+
+
+class Scene(C.Structure):
+    """helio_scene_t (include/helio_b200.h)."""
+    _fields_ = [
+        ("target_pos", C.c_float * 3), ("target_normal", C.c_float * 3), ("plane_u", C.c_float * 3),
+        ("plane_v", C.c_float * 3), ("width", C.c_float), ("height", C.c_float), ("sigma_scale", C.c_float),
+        ("bnd_targ_pos", C.c_float * 3), ("bnd_targ_norm", C.c_float * 3), ("bnd_u", C.c_float * 3),
+        ("bnd_v", C.c_float * 3), ("bnd_width", C.c_float), ("bnd_height", C.c_float),
+    ]
+
+
+class HelioLibError(RuntimeError):
+    pass
+
+
+_lock = threading.Lock()
+_lib = None
+
+
+def build(verbose: bool = False) -> str:
+    """Compile csrc/ -> libhelio_sm100.so for sm_100a (nvcc cross-compiles without a GPU)."""
+    r = subprocess.run(["make", "-C", CSRC], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise HelioLibError("building libhelio_sm100.so failed:\n" + r.stdout + r.stderr)
+    if verbose:
+        print(r.stdout)
+    return LIB_PATH
+
+
+def _declare(lib):
+    p, i, f, i64 = C.c_void_p, C.c_int, C.c_float, C.c_int64
+    sp = C.POINTER(Scene)
+    lib.helio_abi_version.restype = i
+    lib.helio_abi_version.argtypes = []
+    lib.helio_last_error.restype = C.c_char_p
+    lib.helio_last_error.argtypes = []
+    lib.helio_device_ok.restype = i
+    lib.helio_device_ok.argtypes = []
+    lib.helio_geom_workspace_bytes.restype = i64
+    lib.helio_geom_workspace_bytes.argtypes = [i, i]
+    lib.helio_geom_fwd.restype = i
+    lib.helio_geom_fwd.argtypes = [sp, p, p, p, p, i, i, p, p, p, p, p, p, p, p, i64, p]
+    lib.helio_geom_bwd.restype = i
+    lib.helio_geom_bwd.argtypes = [sp, p, p, p, p, i, i, p, p, p, p, p, p, p, p]
+    lib.helio_splat_fwd.restype = i
+    lib.helio_splat_fwd.argtypes = [p, i, i, i, f, f, p, i, p]
+    lib.helio_splat_bwd.restype = i
+    lib.helio_splat_bwd.argtypes = [p, p, i, i, i, f, f, p, i, p]
+    lib.helio_image_max.restype = i
+    lib.helio_image_max.argtypes = [p, i, i, p, p]
+    lib.helio_loss_fwd.restype = i
+    lib.helio_loss_fwd.argtypes = [p, p, p, p, i, i, p, p]
+    lib.helio_loss_bwd.restype = i
+    lib.helio_loss_bwd.argtypes = [p, p, p, p, p, p, i, i, p, p]
+
+
+def load(build_if_missing: bool = False):
+    """Return the loaded library; raise HelioLibError if it cannot be loaded (no fallback)."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            if not build_if_missing:
+                raise HelioLibError(
+                    f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                    "or `make -C doodle_b200/csrc`.  doodle_b200 has no CPU / PyTorch fallback.")
+            build()
+        try:
+            lib = C.CDLL(LIB_PATH)
+        except OSError as e:  # pragma: no cover
+            raise HelioLibError(f"cannot load {LIB_PATH}: {e}") from e
+        for name in EXPORTS:
+            if not hasattr(lib, name):
+                raise HelioLibError(f"{LIB_PATH} does not export {name}")
+        _declare(lib)
+        if lib.helio_abi_version() != ABI_VERSION:
+            raise HelioLibError(f"ABI mismatch: library {lib.helio_abi_version()} != binding {ABI_VERSION}")
+        _lib = lib
+        return lib
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = load().helio_last_error().decode(errors="replace")
+        raise HelioLibError(f"{what} failed (rc={rc}): {msg}")

@@ -1,0 +1,177 @@
+// extern "C" entry points of libhelio_sm100.so (see include/helio_b200.h for the contract).
+#include <mutex>
+
+#include "geom.cuh"
+#include "loss.cuh"
+#include "splat_simt.cuh"
+#include "splat_tc.cuh"
+
+using namespace helio;
+
+namespace {
+
+struct DeviceInfo {
+    int ok = 0;
+    int sms = 0;
+    int cc_major = 0, cc_minor = 0;
+};
+
+// per-device capability cache (one process per GPU is the deployment model, but stay correct
+// if a process touches several devices)
+const DeviceInfo* device_info() {
+    static DeviceInfo info[64];
+    static std::once_flag once[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    std::call_once(once[dev], [dev]() {
+        cudaDeviceProp p;
+        if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) return;
+        info[dev].sms = p.multiProcessorCount;
+        info[dev].cc_major = p.major;
+        info[dev].cc_minor = p.minor;
+        info[dev].ok = (p.major == 10);
+    });
+    return &info[dev];
+}
+
+int require_device(const DeviceInfo** out) {
+    const DeviceInfo* d = device_info();
+    if (d == nullptr) return set_error(HELIO_E_NOSM100, "no usable CUDA device (%s)%s", cudaGetErrorString(cudaGetLastError()));
+    if (!d->ok) {
+        char cc[32];
+        snprintf(cc, sizeof cc, "%d.%d", d->cc_major, d->cc_minor);
+        return set_error(HELIO_E_NOSM100, "libhelio_sm100 is built for sm_100a only; device is cc %s%s", cc);
+    }
+    *out = d;
+    return 0;
+}
+
+inline unsigned geom_blocks(int B, int N) { return (unsigned)(((long long)B * N + kGeomThreads - 1) / kGeomThreads); }
+
+}  // namespace
+
+extern "C" {
+
+HELIO_API int helio_abi_version(void) { return HELIO_ABI_VERSION; }
+
+HELIO_API const char* helio_last_error(void) { return last_error_buf(); }
+
+HELIO_API int helio_device_ok(void) {
+    const DeviceInfo* d = nullptr;
+    return require_device(&d) == 0 ? 1 : 0;
+}
+
+HELIO_API int64_t helio_geom_workspace_bytes(int B, int N) {
+    if (B <= 0 || N <= 0) return 0;
+    return (int64_t)sizeof(GeomWorkspace) + (int64_t)geom_blocks(B, N) * 2 * sizeof(float);
+}
+
+HELIO_API int helio_geom_fwd(const helio_scene_t* scene, const float* helio_pos, const float* sun, const float* action,
+                   const float* errs, int B, int N, float* params, float* actual, float* refl, float* ideal,
+                   float* bounds, float* angles, float* sums, void* workspace, int64_t workspace_bytes, void* stream) {
+    const DeviceInfo* d = nullptr;
+    if (int rc = require_device(&d)) return rc;
+    HELIO_REQUIRE(scene && helio_pos && sun && action && params && actual && refl, "null pointer");
+    HELIO_REQUIRE(B > 0 && N > 0, "B, N must be positive");
+    if (sums) {
+        HELIO_REQUIRE(workspace != nullptr, "sums requested without workspace");
+        if (workspace_bytes < helio_geom_workspace_bytes(B, N))
+            return set_error(HELIO_E_WORKSPACE, "geom workspace too small%s%s");
+    }
+    geom_fwd_kernel<<<geom_blocks(B, N), kGeomThreads, 0, (cudaStream_t)stream>>>(
+        make_scene(scene), helio_pos, sun, action, errs, B, N, reinterpret_cast<float4*>(params), actual, refl, ideal,
+        bounds, angles, sums, reinterpret_cast<GeomWorkspace*>(workspace));
+    HELIO_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+HELIO_API int helio_geom_bwd(const helio_scene_t* scene, const float* helio_pos, const float* sun, const float* action,
+                   const float* errs, int B, int N, const float* g_moments, const float* g_actual, const float* g_refl,
+                   const float* g_bounds, const float* g_angles, const float* g_sums, float* g_action, void* stream) {
+    const DeviceInfo* d = nullptr;
+    if (int rc = require_device(&d)) return rc;
+    HELIO_REQUIRE(scene && helio_pos && sun && action && g_action, "null pointer");
+    HELIO_REQUIRE(B > 0 && N > 0, "B, N must be positive");
+    geom_bwd_kernel<<<geom_blocks(B, N), kGeomThreads, 0, (cudaStream_t)stream>>>(
+        make_scene(scene), helio_pos, sun, action, errs, B, N, reinterpret_cast<const float4*>(g_moments), g_actual,
+        g_refl, g_bounds, g_angles, g_sums, g_action);
+    HELIO_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+HELIO_API int helio_splat_fwd(const float* params, int B, int N, int R, float width, float height, float* img, int impl,
+                    void* stream) {
+    const DeviceInfo* d = nullptr;
+    if (int rc = require_device(&d)) return rc;
+    HELIO_REQUIRE(params && img, "null pointer");
+    HELIO_REQUIRE(B > 0 && N > 0 && R > 0, "B, N, R must be positive");
+    HELIO_REQUIRE(impl >= HELIO_SPLAT_AUTO && impl <= HELIO_SPLAT_TC, "unknown impl");
+    const bool tc_ok = splat_tc_fwd_supported(B, N, R);
+    if (impl == HELIO_SPLAT_TC && !tc_ok)
+        return set_error(HELIO_E_BADARG, "tcgen05 splat forward does not support this shape%s%s");
+    if (impl == HELIO_SPLAT_TC || (impl == HELIO_SPLAT_AUTO && tc_ok && splat_tc_fwd_preferred(B, N, R))) {
+        HELIO_CUDA_OK(splat_tc_fwd(params, img, B, N, R, width, height, d->sms, (cudaStream_t)stream));
+    } else {
+        HELIO_CUDA_OK(splat_fwd_simt(params, img, B, N, R, width, height, d->sms, (cudaStream_t)stream));
+    }
+    return 0;
+}
+
+HELIO_API int helio_splat_bwd(const float* params, const float* g_img, int B, int N, int R, float width, float height,
+                    float* moments, int impl, void* stream) {
+    const DeviceInfo* d = nullptr;
+    if (int rc = require_device(&d)) return rc;
+    HELIO_REQUIRE(params && g_img && moments, "null pointer");
+    HELIO_REQUIRE(B > 0 && N > 0 && R > 0, "B, N, R must be positive");
+    HELIO_REQUIRE(impl >= HELIO_SPLAT_AUTO && impl <= HELIO_SPLAT_TC, "unknown impl");
+    const bool tc_ok = splat_tc_bwd_supported(B, N, R);
+    if (impl == HELIO_SPLAT_TC && !tc_ok)
+        return set_error(HELIO_E_BADARG, "tcgen05 splat backward does not support this shape%s%s");
+    if (impl == HELIO_SPLAT_TC || (impl == HELIO_SPLAT_AUTO && tc_ok && splat_tc_bwd_preferred(B, N, R))) {
+        HELIO_CUDA_OK(splat_tc_bwd(params, g_img, moments, B, N, R, width, height, d->sms, (cudaStream_t)stream));
+    } else {
+        HELIO_CUDA_OK(splat_bwd_simt(params, g_img, moments, B, N, R, width, height, d->sms, (cudaStream_t)stream));
+    }
+    return 0;
+}
+
+HELIO_API int helio_image_max(const float* target, int B, int R, float* tx, void* stream) {
+    const DeviceInfo* d = nullptr;
+    if (int rc = require_device(&d)) return rc;
+    HELIO_REQUIRE(target && tx, "null pointer");
+    HELIO_REQUIRE(B > 0 && R > 0, "B, R must be positive");
+    image_max_kernel<<<B, kLossThreads, 0, (cudaStream_t)stream>>>(target, R, tx);
+    HELIO_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+HELIO_API int helio_loss_fwd(const float* img, const float* target, const float* dmaps, const float* tx, int B, int R,
+                   float* per_img, void* stream) {
+    const DeviceInfo* d = nullptr;
+    if (int rc = require_device(&d)) return rc;
+    HELIO_REQUIRE(img && target && dmaps && tx && per_img, "null pointer");
+    HELIO_REQUIRE(B > 0 && R > 0, "B, R must be positive");
+    loss_fwd_kernel<<<B, kLossThreads, 0, (cudaStream_t)stream>>>(img, target, dmaps, tx, R, per_img);
+    HELIO_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+HELIO_API int helio_loss_bwd(const float* img, const float* target, const float* dmaps, const float* tx, const float* g_per_img,
+                   const float* g_img_in, int B, int R, float* g_img, void* stream) {
+    const DeviceInfo* d = nullptr;
+    if (int rc = require_device(&d)) return rc;
+    HELIO_REQUIRE(img && target && dmaps && tx && g_per_img && g_img, "null pointer");
+    HELIO_REQUIRE(B > 0 && R > 0, "B, R must be positive");
+    // enough CTAs to fill the machine even for small B
+    const size_t vecs = ((size_t)R * R + 3) / 4;
+    int slices = (int)((vecs + 4 * kLossThreads - 1) / (4 * kLossThreads));
+    const int want = (2 * d->sms + B - 1) / B;
+    if (slices > want) slices = want;
+    if (slices < 1) slices = 1;
+    loss_bwd_kernel<<<(unsigned)((long long)B * slices), kLossThreads, 0, (cudaStream_t)stream>>>(
+        img, target, dmaps, tx, g_per_img, g_img_in, R, slices, g_img);
+    HELIO_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,310 @@
+"""HelioEnv -- API mirror of the reference's Gym-style environment on top of the sm_100a kernels.
+
+Mirrors ``test_environment.HelioEnv`` (reference test_environment.py:175-526): same constructor
+signature and defaults, same RNG draw order at construction / reset, same ``reset`` / ``step``
+return contracts (obs{'img','aux'}, metrics{'mse','dist','bound','alignment_loss'} with grad,
+monitor{...}).  The setup-time pieces the scope table leaves in Python (sun-cone sampling, scipy
+EDT distance maps) are restated here; the per-step work runs in K1-K4.
+
+Differences, all opt-in or bug-compatible:
+  * ``new_sun_pos_every_reset=True`` works (the reference calls a method that does not exist,
+    test_environment.py:379);
+  * the six NaN/Inf asserts (test_environment.py:495-501) read ONE fused device flag (one sync);
+  * ``cache_target`` (keyword-only extension, default False = re-render the target every step as
+    the reference does, test_environment.py:429-435).  The target only depends on ``sun_pos``, so
+    caching it is exact.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+from scipy.ndimage import distance_transform_edt
+
+from .field import HelioField
+from .functional import ImageLossFn, image_max, require_cuda
+
+try:  # gymnasium is optional: only Env / spaces.Box / spaces.Dict are touched (test_environment.py:11-12)
+    import gymnasium as gym
+    from gymnasium import spaces
+    _EnvBase = gym.Env
+except Exception:  # pragma: no cover - gymnasium is not installed in the build image
+    gym = None
+    _EnvBase = object
+
+    class _Box:
+        def __init__(self, low=None, high=None, shape=None, dtype=None):
+            self.low, self.high, self.shape, self.dtype = low, high, shape, dtype
+
+    class _Dict(dict):
+        def __init__(self, d):
+            super().__init__(d)
+
+    class spaces:  # noqa: N801 - mirrors the gymnasium module name
+        Box = _Box
+        Dict = _Dict
+
+
+# ----------------------------------------------------------------------------------------------
+# host-side helpers (setup time; device-agnostic so they are testable without a GPU)
+# ----------------------------------------------------------------------------------------------
+def azimuth_elevation_to_primary_direction(azimuth_deg: float, elevation_deg: float, device=None) -> torch.Tensor:
+    """Unit direction for (azimuth, elevation) in degrees (test_environment.py:18-40)."""
+    az = math.radians(azimuth_deg)
+    el = math.radians(elevation_deg)
+    vec = torch.tensor([math.cos(el) * math.cos(az), math.cos(el) * math.sin(az), math.sin(el)],
+                       dtype=torch.float32, device=device)
+    return vec / torch.norm(vec)
+
+
+def sample_cone_directions(n: int, axis: torch.Tensor, half_angle_deg: float, device=None,
+                           force_upper_hemisphere: bool = False) -> torch.Tensor:
+    """n unit vectors uniform on the spherical cap around ``axis`` (test_environment.py:42-88).
+
+    Draw order (two torch.rand(n) calls: cos-theta first, then phi) matches the reference so that a
+    seeded run samples the same suns."""
+    device = device or axis.device
+    a = F.normalize(axis.to(device), dim=0)
+    alpha = math.radians(half_angle_deg)
+    helper = torch.tensor([0.0, 0.0, 1.0], device=device)
+    if torch.abs(a[2]) > 0.999:
+        helper = torch.tensor([0.0, 1.0, 0.0], device=device)
+    u = F.normalize(torch.linalg.cross(helper, a), dim=0)
+    v = torch.linalg.cross(a, u)
+    u01 = torch.rand(n, device=device)
+    cos_theta = 1.0 - u01 * (1.0 - math.cos(alpha))
+    sin_theta = torch.sqrt(torch.clamp(1.0 - cos_theta ** 2, min=0.0))
+    phi = 2.0 * math.pi * torch.rand(n, device=device)
+    dirs = (u[None, :] * (sin_theta * torch.cos(phi))[:, None]
+            + v[None, :] * (sin_theta * torch.sin(phi))[:, None]
+            + a[None, :] * cos_theta[:, None])
+    dirs = F.normalize(dirs, dim=1)
+    if force_upper_hemisphere:
+        dirs[:, 2] = torch.abs(dirs[:, 2])
+    return dirs
+
+
+def make_distance_maps(imgs: torch.Tensor, thr: float = 0.5) -> torch.Tensor:
+    """Per-image Euclidean distance to the >thr*max region (test_environment.py:92-97; scipy EDT on
+    the host, setup time only)."""
+    maps = []
+    for img in imgs.detach().cpu().numpy():
+        mask = (img > thr * img.max()).astype(np.uint8)
+        maps.append(distance_transform_edt(1 - mask))
+    return torch.tensor(np.stack(maps), dtype=torch.float32, device=imgs.device)
+
+
+# ----------------------------------------------------------------------------------------------
+class HelioEnv(_EnvBase):
+
+    def __init__(self,
+                 heliostat_pos,
+                 targ_pos,
+                 targ_area,
+                 targ_norm,
+                 sigma_scale=0.1,
+                 error_scale_mrad=180.0,
+                 initial_action_noise=0.0,
+                 resolution=128,
+                 batch_size=25,
+                 device='cuda',
+                 new_sun_pos_every_reset=False,
+                 new_errors_every_reset=True,
+                 use_error_mask=False,
+                 error_mask_ratio=0.2,
+                 exponential_risk=False,
+                 single_sun=False,
+                 azimuth=45.0,
+                 elevation=45.0,
+                 *,
+                 cache_target=False,
+                 check_finite=True,
+                 ):
+        super().__init__()
+        require_cuda(torch.device(device), "HelioEnv")
+
+        if not isinstance(heliostat_pos, torch.Tensor):
+            heliostat_pos = torch.tensor(heliostat_pos, dtype=torch.float32, device=device)
+        if not isinstance(targ_pos, torch.Tensor):
+            targ_pos = torch.tensor(targ_pos, dtype=torch.float32, device=device)
+        if not isinstance(targ_norm, torch.Tensor):
+            targ_norm = torch.tensor(targ_norm, dtype=torch.float32, device=device)
+
+        self.resolution = resolution
+        self.batch_size = batch_size
+        self.device = device
+
+        self.heliostat_pos = heliostat_pos
+        self.num_heliostats = heliostat_pos.shape[0]
+        self.targ_pos = targ_pos
+        self.targ_area = targ_area
+        self.targ_norm = targ_norm
+        self.azimuth = azimuth
+        self.elevation = elevation
+        self.sigma_scale = sigma_scale
+        self.error_scale_mrad = error_scale_mrad
+        self.initial_action_noise = initial_action_noise
+        self.sun_pos = None
+        self.sun_errors = None
+        self.new_sun_pos_every_reset = new_sun_pos_every_reset
+        self.new_errors_every_reset = new_errors_every_reset
+        self.single_sun = single_sun
+        self.cache_target = cache_target
+        self.check_finite = check_finite
+        self._target_cache = None
+
+        action_dim = heliostat_pos.shape[0] * 3
+        self.action_space = spaces.Box(low=-1.0, high=1.0, shape=(action_dim,), dtype=np.float32)
+        self.observation_space = spaces.Dict({
+            'img': spaces.Box(low=0.0, high=np.inf, shape=(self.batch_size, resolution, resolution), dtype=np.float32),
+            'aux': spaces.Box(low=-np.inf, high=np.inf, shape=(self.batch_size, 3 + self.heliostat_pos.shape[0] * 3),
+                              dtype=np.float32),
+        })
+
+        # two fields, same order as the reference so that seeded error draws line up (:255-277)
+        common = dict(heliostat_positions=self.heliostat_pos, target_position=self.targ_pos, target_area=self.targ_area,
+                      target_normal=self.targ_norm, sigma_scale=self.sigma_scale, resolution=self.resolution,
+                      max_batch_size=self.batch_size, device=self.device)
+        self.ref_field = HelioField(error_scale_mrad=0.0, **common)
+        self.noisy_field = HelioField(error_scale_mrad=self.error_scale_mrad, **common)
+        for f in (self.ref_field, self.noisy_field):
+            f.set_boundary_geometry(self.targ_pos, self.targ_norm, self.targ_area)
+
+        self.use_error_mask = use_error_mask
+        self.error_mask_ratio = error_mask_ratio
+        self.exponential_risk = exponential_risk
+
+        B, N, R = float(self.batch_size), float(self.num_heliostats), float(self.resolution)
+        self._inv_counts = 1.0 / torch.tensor([B * R * R, B, B * N, B * N], dtype=torch.float32, device=self.device)
+
+        self.set_sun_pos(self._sample_sun_pos())
+
+    # ------------------------------------------------------------------ sun positions
+    def _sample_sun_dirs(self) -> torch.Tensor:
+        """Sun directions as sampled in the reference constructor (test_environment.py:286-321)."""
+        half_angle_deg, force_upper = 2.0, True
+        n = 1 if self.single_sun else self.batch_size
+        if self.azimuth is not None and self.elevation is not None:
+            primary = azimuth_elevation_to_primary_direction(self.azimuth, self.elevation, device=self.device)
+            dirs = sample_cone_directions(n=n, axis=primary, half_angle_deg=half_angle_deg, device=self.device,
+                                          force_upper_hemisphere=force_upper)
+        else:
+            dirs = F.normalize(torch.randn(n, 3, device=self.device), dim=1)
+        if self.single_sun:
+            dirs = dirs.repeat(self.batch_size, 1)
+        if self.azimuth is None or self.elevation is None:
+            dirs[:, 2] = torch.abs(dirs[:, 2])
+        return dirs
+
+    def _sample_sun_pos(self) -> torch.Tensor:
+        radius = math.hypot(10000, 10000)                                   # :324
+        return self._sample_sun_dirs() * radius
+
+    def set_sun_pos_from_azimuth_elevation(self, azimuth_deg: float, elevation_deg: float, device=None):
+        """Resample the suns around a new (azimuth, elevation) (the reference's version, :332-357, is
+        unfinished: it never stores the result)."""
+        self.azimuth, self.elevation = azimuth_deg, elevation_deg
+        self.set_sun_pos(self._sample_sun_pos())
+
+    def set_sun_pos(self, sun_positions: torch.Tensor):
+        """Fix the current sun positions and rebuild target-dependent state (:359-370)."""
+        self.sun_pos = sun_positions.clone().detach().to(device=self.device, dtype=torch.float32)
+        self._target_cache = None
+        self.ref_field.init_actions(self.sun_pos)
+        with torch.no_grad():
+            ideal_normals = self.ref_field.calculate_ideal_normals(self.sun_pos)
+            timg, _ = self.ref_field.render(self.sun_pos, self.ref_field.initial_action, ideal_normals)
+        self.distance_maps = make_distance_maps(timg)
+        self.ref_min = torch.min(timg)
+        self.ref_max = torch.max(timg)
+
+    # ------------------------------------------------------------------ reset / step
+    def reset(self):
+        """Returns {'img': [B,R,R], 'aux': [B,3+3N] = cat(sun_pos, ideal normals)} (:372-400)."""
+        if self.new_sun_pos_every_reset:
+            self.set_sun_pos(self._sample_sun_pos())
+        if self.new_errors_every_reset:
+            self.noisy_field.reset_errors()
+        with torch.no_grad():
+            self.noisy_field.init_actions(self.sun_pos)
+            out = self.noisy_field._render_full(self.sun_pos, self.noisy_field.initial_action, want_aux=True)
+        self.ideal_normals = out.ideal
+        aux = torch.cat([self.sun_pos, out.ideal.flatten(1)], dim=1)
+        return {'img': out.img, 'aux': aux}
+
+    def _target(self, ideal: torch.Tensor):
+        """Target image of the error-free field and its per-image max (:429-436)."""
+        if self.cache_target and self._target_cache is not None:
+            return self._target_cache
+        with torch.no_grad():
+            target = self.ref_field._render_full(self.sun_pos, ideal, want_aux=False).img
+            tx = image_max(target)
+        if self.cache_target:
+            self._target_cache = (target, tx)
+        return target, tx
+
+    def _quantile_cutoff(self, avg_error_per_heatmap: torch.Tensor) -> torch.Tensor:
+        """Global quantile over the batch (:445); the sharded env overrides this with an all-gather."""
+        return torch.quantile(avg_error_per_heatmap, 1 - self.error_mask_ratio)
+
+    def _reduce_means(self, sums: torch.Tensor) -> torch.Tensor:
+        """Packed {sum sq, sum dist, sum bound, sum angle} -> the four means (:128,455-457); the sharded
+        env all-reduces here."""
+        return sums * self._inv_counts
+
+    def step(self, action):
+        """obs, metrics, monitor = step(action)   (:402-516).  action: [B, 3N] or [B, N, 3]."""
+        if isinstance(action, np.ndarray):
+            action = torch.tensor(action, dtype=torch.float32, device=self.device)
+        B, N, R = self.batch_size, self.num_heliostats, self.resolution
+
+        out = self.noisy_field._render_full(self.sun_pos, action, want_aux=True)     # K1 + K2
+        img, ideal_normals = out.img, out.ideal
+        aux = torch.cat([self.sun_pos.detach(), action.flatten(1)], dim=1)
+
+        target, tx = self._target(ideal_normals)
+        per_img = ImageLossFn.apply(img, target, self.distance_maps, tx)             # K4: [B,3]
+        avg_error_per_heatmap = per_img[:, 2] / float(R * R)
+        if self.use_error_mask:                                                      # :445-452
+            cutoff = self._quantile_cutoff(avg_error_per_heatmap)
+            mask = (avg_error_per_heatmap > cutoff).float()
+            sq, ds = per_img[:, 0] * mask, per_img[:, 1] * mask
+        else:
+            sq, ds = per_img[:, 0], per_img[:, 1]
+
+        if not self.exponential_risk:                                                # :464-480
+            bound_sum = out.sums[0]
+        else:
+            bound_sum = torch.exp(out.bounds + 1e-6).sum()
+        packed = torch.stack([sq.sum(), ds.sum(), bound_sum, out.sums[1]])
+        means = self._reduce_means(packed)
+        mse, dist_l, bound, alignment_loss = means[0], means[1], means[2], means[3]
+
+        if self.check_finite:                                                        # :495-501, one sync
+            if not bool(torch.isfinite(means[:3]).all()):
+                assert not torch.isnan(mse).any(), "MSE is NaN"
+                assert not torch.isnan(dist_l).any(), "Distance loss is NaN"
+                assert not torch.isnan(bound).any(), "Boundary loss is NaN"
+                assert not torch.isinf(mse).any(), "MSE is Inf"
+                assert not torch.isinf(dist_l).any(), "Distance loss is Inf"
+                assert not torch.isinf(bound).any(), "Boundary loss is Inf"
+
+        metrics = {'mse': mse, 'dist': dist_l, 'bound': bound, 'alignment_loss': alignment_loss}
+        obs = {'img': img, 'aux': aux}
+        monitor = {
+            'normals': action.view(self.batch_size, -1, 3),
+            'reflected_rays': out.refl.view([-1, 3]),
+            'ideal_normals': ideal_normals.view([-1, 3]),
+            'all_bounds': out.bounds,
+            'mae_image': avg_error_per_heatmap.view([-1, 1]),
+            'alignment_errors': out.angles.detach().view([-1]),
+        }
+        return obs, metrics, monitor
+
+    def seed(self, seed=None):
+        """torch + numpy seeds (:518-526)."""
+        if seed is not None:
+            torch.manual_seed(seed)
+            np.random.seed(seed)

@@ -1,0 +1,211 @@
+"""torch.autograd.Function wrappers over the C ABI (include/helio_b200.h).
+
+PyTorch is plumbing here: it owns device memory, the current stream and the autograd tape; every
+number is produced by the kernels in libhelio_sm100.so.  Nothing in this module has a CPU path.
+
+Graph for one differentiable render (HelioField.render, newenv_rl_test_multi_error.py:308-415):
+
+    action --GeomFn--> params --SplatFn--> img
+                   \\-> actual, refl, bounds, angles, sums
+
+SplatFn.backward hands the per-(b,n) moments {S0,Sx,Sy,S2} of g*G to GeomFn.backward as the
+"gradient" of ``params``; GeomFn.backward turns them into dL/daction (see include/helio_b200.h).
+``params`` is an internal tensor, never exposed to callers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import SPLAT_AUTO, SPLAT_SIMT, SPLAT_TC, Scene  # noqa: F401
+
+
+# ---- launch accounting / live per-kernel timing (bench.py reads these) ------------------------
+_LAUNCHES = 0
+_PROFILE = {"on": False, "events": []}
+
+
+def launch_count() -> int:
+    """Number of libhelio kernels launched by this process so far (one per C-ABI compute call)."""
+    return _LAUNCHES
+
+
+def reset_profile(enabled: bool):
+    _PROFILE["on"] = bool(enabled)
+    _PROFILE["events"] = []
+
+
+def collect_profile():
+    """{kernel: {n, total_ms, avg_ms}} from CUDA events recorded around each call on its stream."""
+    torch.cuda.synchronize()
+    out = {}
+    for name, e0, e1 in _PROFILE["events"]:
+        d = out.setdefault(name, dict(n=0, total_ms=0.0))
+        d["n"] += 1
+        d["total_ms"] += e0.elapsed_time(e1)
+    for d in out.values():
+        d["avg_ms"] = d["total_ms"] / d["n"]
+    return out
+
+
+class _Call:
+    """Context manager around one C-ABI launch: device guard, launch count, optional CUDA events."""
+
+    def __init__(self, name: str, device: torch.device):
+        self.name, self.guard = name, torch.cuda.device(device)
+
+    def __enter__(self):
+        global _LAUNCHES
+        self.guard.__enter__()
+        _LAUNCHES += 1
+        if _PROFILE["on"]:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if _PROFILE["on"]:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            _PROFILE["events"].append((self.name, self.e0, e1))
+        return self.guard.__exit__(*exc)
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _cf(t: torch.Tensor) -> torch.Tensor:
+    """contiguous fp32 (mirrors torch.as_tensor(..., float32), newenv_rl_test_multi_error.py:326,334)."""
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def require_cuda(device: torch.device, what: str):
+    if device.type != "cuda":
+        raise RuntimeError(f"{what}: doodle_b200 runs on sm_100a GPUs only and has no CPU fallback (got device={device})")
+    if not torch.cuda.is_available():
+        raise RuntimeError(f"{what}: CUDA is not available; doodle_b200 has no CPU fallback")
+
+
+class GeomFn(torch.autograd.Function):
+    """K1: action -> (params, actual, refl[, ideal, bounds, angles, sums])."""
+
+    @staticmethod
+    def forward(ctx, action, sun, errs, helio, scene, workspace, want_aux: bool):
+        lib = _lib.load()
+        B, N = sun.shape[0], helio.shape[0]
+        dev = action.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        params = torch.empty(B, N, 4, **f32)
+        actual = torch.empty(B, N, 3, **f32)
+        refl = torch.empty(B * N, 3, **f32)
+        ideal = bounds = angles = sums = None
+        if want_aux:
+            ideal = torch.empty(B, N, 3, **f32)
+            bounds = torch.empty(B, N, **f32)
+            angles = torch.empty(B, N, **f32)
+            sums = torch.empty(2, **f32)
+        with _Call("geom_fwd", dev):
+            rc = lib.helio_geom_fwd(C.byref(scene), _ptr(helio), _ptr(sun), _ptr(action), _ptr(errs), B, N,
+                                    _ptr(params), _ptr(actual), _ptr(refl), _ptr(ideal), _ptr(bounds), _ptr(angles),
+                                    _ptr(sums), _ptr(workspace), workspace.numel() * workspace.element_size() if workspace is not None else 0,
+                                    _stream())
+        _lib.check(rc, "helio_geom_fwd")
+        ctx.save_for_backward(action, sun, errs, helio)
+        ctx.scene = scene
+        ctx.set_materialize_grads(False)
+        if want_aux:
+            ctx.mark_non_differentiable(ideal)
+        return params, actual, refl, ideal, bounds, angles, sums
+
+    @staticmethod
+    def backward(ctx, g_params, g_actual, g_refl, g_ideal, g_bounds, g_angles, g_sums):
+        lib = _lib.load()
+        action, sun, errs, helio = ctx.saved_tensors
+        B, N = sun.shape[0], helio.shape[0]
+        gs = [None if g is None else _cf(g) for g in (g_params, g_actual, g_refl, g_bounds, g_angles, g_sums)]
+        g_action = torch.empty_like(action)
+        with _Call("geom_bwd", action.device):
+            rc = lib.helio_geom_bwd(C.byref(ctx.scene), _ptr(helio), _ptr(sun), _ptr(action), _ptr(errs), B, N,
+                                    *[_ptr(g) for g in gs], _ptr(g_action), _stream())
+        _lib.check(rc, "helio_geom_bwd")
+        return g_action, None, None, None, None, None, None
+
+
+class SplatFn(torch.autograd.Function):
+    """K2/K3: params -> img[B,R,R]; backward returns the moments tensor in the slot of params."""
+
+    @staticmethod
+    def forward(ctx, params, R: int, width: float, height: float, impl: int):
+        lib = _lib.load()
+        B, N = params.shape[0], params.shape[1]
+        img = torch.empty(B, R, R, dtype=torch.float32, device=params.device)
+        with _Call("splat_fwd", params.device):
+            rc = lib.helio_splat_fwd(_ptr(params), B, N, R, width, height, _ptr(img), impl, _stream())
+        _lib.check(rc, "helio_splat_fwd")
+        ctx.save_for_backward(params)
+        ctx.cfg = (R, width, height, impl)
+        return img
+
+    @staticmethod
+    def backward(ctx, g_img):
+        lib = _lib.load()
+        (params,) = ctx.saved_tensors
+        R, width, height, impl = ctx.cfg
+        B, N = params.shape[0], params.shape[1]
+        g_img = _cf(g_img)
+        moments = torch.empty_like(params)
+        with _Call("splat_bwd", params.device):
+            rc = lib.helio_splat_bwd(_ptr(params), _ptr(g_img), B, N, R, width, height, _ptr(moments), impl, _stream())
+        _lib.check(rc, "helio_splat_bwd")
+        return moments, None, None, None, None
+
+
+def image_max(target: torch.Tensor) -> torch.Tensor:
+    """tx[b] = max(target[b]).clamp_min(1e-6)  (test_environment.py:436)."""
+    lib = _lib.load()
+    target = _cf(target)
+    B, R = target.shape[0], target.shape[-1]
+    tx = torch.empty(B, dtype=torch.float32, device=target.device)
+    with _Call("image_max", target.device):
+        rc = lib.helio_image_max(_ptr(target), B, R, _ptr(tx), _stream())
+    _lib.check(rc, "helio_image_max")
+    return tx
+
+
+class ImageLossFn(torch.autograd.Function):
+    """K4: img -> per_img[B,3] = {sum diff^2, sum |diff| dmaps, sum |diff|}, diff=(img-target)/tx."""
+
+    @staticmethod
+    def forward(ctx, img, target, dmaps, tx):
+        lib = _lib.load()
+        img = _cf(img)
+        B, R = img.shape[0], img.shape[-1]
+        per_img = torch.empty(B, 3, dtype=torch.float32, device=img.device)
+        with _Call("loss_fwd", img.device):
+            rc = lib.helio_loss_fwd(_ptr(img), _ptr(target), _ptr(dmaps), _ptr(tx), B, R, _ptr(per_img), _stream())
+        _lib.check(rc, "helio_loss_fwd")
+        ctx.save_for_backward(img, target, dmaps, tx)
+        return per_img
+
+    @staticmethod
+    def backward(ctx, g_per_img):
+        lib = _lib.load()
+        img, target, dmaps, tx = ctx.saved_tensors
+        B, R = img.shape[0], img.shape[-1]
+        g_per_img = _cf(g_per_img)
+        g_img = torch.empty_like(img)
+        with _Call("loss_bwd", img.device):
+            rc = lib.helio_loss_bwd(_ptr(img), _ptr(target), _ptr(dmaps), _ptr(tx), _ptr(g_per_img), None, B, R,
+                                    _ptr(g_img), _stream())
+        _lib.check(rc, "helio_loss_bwd")
+        return g_img, None, None, None

@@ -1,0 +1,139 @@
+/* helio_b200.h -- C ABI of libhelio_sm100.so: the DOODLE flux-renderer hot path on B200 (sm_100a).
+ *
+ * Drop-in boundary for ONE path of l3th4l/DOODLE: HelioField.render forward+backward and the
+ * HelioEnv.step loss block.  The reference is pure Python/PyTorch and has no FFI of its own; each
+ * entry point below names the reference Python it replaces (file:line relative to the reference
+ * root).  INTEGRATION.md shows the ctypes binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer to contiguous fp32 unless the name ends in _host;
+ *  - the library never allocates, frees or keeps pointers: the caller owns all buffers
+ *    (outputs and workspaces included), so every call is CUDA-graph capturable;
+ *  - calls only enqueue work on `stream` (a cudaStream_t passed as void*); no implicit sync;
+ *  - return 0 on success, a positive cudaError_t or a negative HELIO_E_* code otherwise; the
+ *    message is available from helio_last_error() (thread-local);
+ *  - B = suns / episodes, N = heliostats, R = receiver resolution; images are [B][R][R] with
+ *    axis 1 <-> plane_u (x, width) and axis 2 <-> plane_v (y, height)
+ *    (meshgrid indexing="ij", newenv_rl_test_multi_error.py:129-131).
+ */
+#ifndef HELIO_B200_H
+#define HELIO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HELIO_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define HELIO_API __attribute__((visibility("default")))
+#else
+#define HELIO_API
+#endif
+
+#define HELIO_E_BADARG   (-1) /* null pointer / non-positive size / unsupported shape */
+#define HELIO_E_NOSM100  (-2) /* device is not compute capability 10.x                 */
+#define HELIO_E_WORKSPACE (-3) /* workspace too small                                   */
+
+/* splat implementation selector */
+#define HELIO_SPLAT_AUTO 0 /* tcgen05 when the shape supports it, else SIMT */
+#define HELIO_SPLAT_SIMT 1 /* CUDA-core shared-memory-tiled path             */
+#define HELIO_SPLAT_TC   2 /* tcgen05 3xTF32 path (error if unsupported)     */
+
+/* Scene constants of one HelioField (newenv_rl_test_multi_error.py:162-216) plus the constants
+ * HelioEnv.step hands to boundary() (test_environment.py:460-470).  Plain floats, passed by
+ * pointer from HOST memory. */
+typedef struct helio_scene {
+    float target_pos[3];    /* HelioField.target_position                                  */
+    float target_normal[3]; /* HelioField.target_normal, unit length (:189-192)            */
+    float plane_u[3];       /* :206                                                        */
+    float plane_v[3];       /* :207-213                                                    */
+    float width, height;    /* target_area (:187)                                          */
+    float sigma_scale;      /* :197                                                        */
+    /* boundary(): HelioEnv passes ITS OWN targ_pos/targ_norm (not normalised) and the fixed
+     * east/up axes (1,0,0)/(0,0,1) (test_environment.py:461-470). */
+    float bnd_targ_pos[3];
+    float bnd_targ_norm[3];
+    float bnd_u[3];
+    float bnd_v[3];
+    float bnd_width, bnd_height;
+} helio_scene_t;
+
+HELIO_API int helio_abi_version(void);
+HELIO_API const char* helio_last_error(void);
+/* 1 if the current device can run the kernels (cc 10.x), else 0 (and last_error is set). */
+HELIO_API int helio_device_ok(void);
+
+/* Bytes of workspace helio_geom_fwd needs for (B, N) (block partials + ticket counter).  The
+ * workspace must be zero-initialised ONCE by the caller; the kernel leaves it zeroed. */
+HELIO_API int64_t helio_geom_workspace_bytes(int B, int N);
+
+/* K1 forward.  Replaces, fused per (b, n):
+ *   rotate_normals_batch            newenv_rl_test_multi_error.py:78-104
+ *   Up-axis leaky-ReLU + normalise  :369-373
+ *   incident dir, reflect_vectors   :376-383, :46-50
+ *   ray_plane_intersection_batch    :52-75
+ *   sigma from distance             :126-127, :146
+ *   calculate_ideal_normals         :256-278          (ideal, optional)
+ *   boundary(return_all=True)       test_environment.py:101-130   (bounds, optional)
+ *   calculate_angles_mrad           test_environment.py:132-155   (angles, optional)
+ * in : helio[N][3], sun[B][3], action[B][N][3], errs[B][N][2] in mrad (NULL = zero errors)
+ * out: params[B][N][4] = {a, b, k2, amp}: the heliostat's footprint on the receiver is
+ *        amp * exp2(-k2 (x_i - a)^2) * exp2(-k2 (y_j - b)^2)   (k2 = log2(e)/max(2 sigma^2,1e-12);
+ *        an invalid ray has k2 = 0, amp = 1: +1 on every pixel, :141-143)
+ *      actual[B][N][3], refl[B][N][3] (= reflected_rays [B*N][3]);
+ *      ideal[B][N][3], bounds[B][N], angles[B][N] may each be NULL;
+ *      sums[2] = {sum bounds, sum angles} (warp-shuffle + ordered block reduction; NULL to skip,
+ *      needs `workspace`). */
+HELIO_API int helio_geom_fwd(const helio_scene_t* scene_host, const float* helio, const float* sun,
+                   const float* action, const float* errs, int B, int N,
+                   float* params, float* actual, float* refl, float* ideal,
+                   float* bounds, float* angles, float* sums,
+                   void* workspace, int64_t workspace_bytes, void* stream);
+
+/* K1 backward (recomputes the forward chain; what autograd does for the ops listed above).
+ * g_moments[B][N][4] = {S0,Sx,Sy,S2} from helio_splat_bwd; g_actual, g_refl [B][N][3];
+ * g_bounds, g_angles [B][N]; g_sums[2] (device) = upstream grads of sums.  Any may be NULL.
+ * out: g_action[B][N][3] (overwritten). */
+HELIO_API int helio_geom_bwd(const helio_scene_t* scene_host, const float* helio, const float* sun,
+                   const float* action, const float* errs, int B, int N,
+                   const float* g_moments, const float* g_actual, const float* g_refl,
+                   const float* g_bounds, const float* g_angles, const float* g_sums,
+                   float* g_action, void* stream);
+
+/* K2: Gaussian flux splat + sum over heliostats.  Replaces gaussian_blur_batch
+ * (newenv_rl_test_multi_error.py:107-149) and images = gauss.sum(1) (:404-406) without
+ * materialising [B][N][R][R]:  img[b] = Gx^T diag(amp) Gy.
+ * impl: HELIO_SPLAT_*.  img[B][R][R] is overwritten. */
+HELIO_API int helio_splat_fwd(const float* params, int B, int N, int R, float width, float height,
+                    float* img, int impl, void* stream);
+
+/* K3: adjoint of K2 w.r.t. the footprint parameters, recomputing the Gaussians.
+ * in : params[B][N][4], g_img[B][R][R]
+ * out: moments[B][N][4] = { S0 = sum g G, Sx = sum g G (x_i-a), Sy = sum g G (y_j-b),
+ *                           S2 = sum g G ((x_i-a)^2 + (y_j-b)^2) },  G = amp Gx_i Gy_j. */
+HELIO_API int helio_splat_bwd(const float* params, const float* g_img, int B, int N, int R,
+                    float width, float height, float* moments, int impl, void* stream);
+
+/* tx[b] = max(max_ij target[b], 1e-6)   (test_environment.py:436). */
+HELIO_API int helio_image_max(const float* target, int B, int R, float* tx, void* stream);
+
+/* K4 forward: per-image loss partials of HelioEnv.step (test_environment.py:438-457,492):
+ *   diff = (img - target)/tx ;  per_img[b] = { sum diff^2, sum |diff| dmaps, sum |diff| }.
+ * The caller forms mse = sum_b per_img[b][0]/(B R^2), dist = mean_b per_img[b][1],
+ * mae_image[b] = per_img[b][2]/R^2 (and the error-mask variants) from per_img[B][3]. */
+HELIO_API int helio_loss_fwd(const float* img, const float* target, const float* dmaps, const float* tx,
+                   int B, int R, float* per_img, void* stream);
+
+/* K4 backward: g_img = (2 g0 diff + (g1 dmaps + g2) sign(diff)) / tx with g_per_img[B][3] =
+ * {g0,g1,g2}; g_img_in (NULL or [B][R][R]) is added (gradient arriving through obs['img']). */
+HELIO_API int helio_loss_bwd(const float* img, const float* target, const float* dmaps, const float* tx,
+                   const float* g_per_img, const float* g_img_in, int B, int R, float* g_img,
+                   void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HELIO_B200_H */

@@ -32,6 +32,7 @@ from concurrent.futures import ThreadPoolExecutor
 import numpy as np
 
 LEAKY_SLOPE = 0.01  # F.leaky_relu default, newenv_rl_test_multi_error.py:369
+_NCHUNK = 64         # heliostats per temporary block (memory bound only)
 
 
 # ----------------------------------------------------------------------------
@@ -205,10 +206,15 @@ def render_forward(sun, action, errs, helio, target_pos, target_normal, target_a
 
     def one(b):
         # gaussian_blur_batch :140-148 for the N heliostats of sun b, then sum over N :406
-        diffs = (pts[None] - P[b][:, None, None, :]) * vm[b][:, None, None, :]
-        dist_sq = (diffs * diffs).sum(axis=3)
-        G = np.exp(-dist_sq / ts2[b][:, None, None])
-        images[b] = G.sum(axis=0)
+        # (heliostats in chunks only to bound the [n,R,R,3] temporaries; the arithmetic is unchanged)
+        acc = np.zeros((R, R), dtype=dtype)
+        for n0 in range(0, N, _NCHUNK):
+            s = slice(n0, min(N, n0 + _NCHUNK))
+            diffs = (pts[None] - P[b][s, None, None, :]) * vm[b][s, None, None, :]
+            dist_sq = (diffs * diffs).sum(axis=3)
+            G = np.exp(-dist_sq / ts2[b][s, None, None])
+            acc += G.sum(axis=0)
+        images[b] = acc
 
     th = threads or _threads()
     if th > 1 and B > 1:
@@ -247,14 +253,16 @@ def render_backward(ctx, g_img=None, g_actual=None, g_refl=None, threads=None):
         gts = g_ts2.reshape(B, N)
 
         def one(b):
-            diffs = (pts[None] - P[b][:, None, None, :]) * vm[b][:, None, None, :]
-            dist_sq = (diffs * diffs).sum(axis=3)
-            G = np.exp(-dist_sq / ts2[b][:, None, None])
-            gG = g_img[b][None] * G                                   # dL/d(exp arg)
-            g_dsq = -gG / ts2[b][:, None, None]
-            gts[b] = (gG * dist_sq).sum(axis=(1, 2)) / (ts2[b] * ts2[b])
-            g_diffs = dtype(2) * diffs * g_dsq[..., None] * vm[b][:, None, None, :]
-            gP3[b] = -g_diffs.sum(axis=(1, 2))
+            for n0 in range(0, N, _NCHUNK):
+                s = slice(n0, min(N, n0 + _NCHUNK))
+                diffs = (pts[None] - P[b][s, None, None, :]) * vm[b][s, None, None, :]
+                dist_sq = (diffs * diffs).sum(axis=3)
+                G = np.exp(-dist_sq / ts2[b][s, None, None])
+                gG = g_img[b][None] * G                               # dL/d(exp arg)
+                g_dsq = -gG / ts2[b][s, None, None]
+                gts[b, s] = (gG * dist_sq).sum(axis=(1, 2)) / (ts2[b][s] * ts2[b][s])
+                g_diffs = dtype(2) * diffs * g_dsq[..., None] * vm[b][s, None, None, :]
+                gP3[b, s] = -g_diffs.sum(axis=(1, 2))
 
         th = threads or _threads()
         if th > 1 and B > 1:

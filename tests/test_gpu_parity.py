@@ -1,0 +1,332 @@
+"""Parity of the sm_100a path against the reference (golden fixtures) and the oracle.  -m gpu.
+
+Tolerances are BASELINE.json's: images rtol 1e-4 / atol 1e-6, action gradients 1e-3 relative
+(max-norm relative: |g - g_ref|_inf / |g_ref|_inf)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, rel_err
+from oracle import helio_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+IMG_TOL = dict(rtol=1e-4, atol=1e-6)
+GRAD_TOL = 1e-3
+RENDER = ["readme", "trainer", "single", "tilted", "wide", "parallel"]
+ENV = ["readme", "trainer", "mask", "exprisk"]
+
+
+def _dev():
+    return torch.device("cuda", 0)
+
+
+def _t(x):
+    return torch.as_tensor(np.asarray(x), device=_dev())
+
+
+def _impls():
+    from doodle_b200 import SPLAT_SIMT, SPLAT_AUTO
+    return [SPLAT_SIMT, SPLAT_AUTO]
+
+
+def _field_from_golden(g, impl):
+    from doodle_b200 import HelioField
+    B = 1 if bool(g["single"]) else g["sun"].reshape(-1, 3).shape[0]
+    f = HelioField(_t(g["helio"]), _t(g["target_pos"]), tuple(float(x) for x in g["area"]), _t(g["target_normal"]),
+                   error_scale_mrad=float(g["err_mrad"]), sigma_scale=float(g["sigma_scale"]), resolution=int(g["R"]),
+                   device="cuda:0", max_batch_size=max(B, 1))
+    f.error_angles_mrad = _t(g["error_angles_mrad"])           # same trick as newenv/sanity_check_multi_error.py:84-87
+    f.batch_error_angles_mrad = _t(g["batch_error_angles_mrad"])
+    f.splat_impl = impl
+    return f
+
+
+@pytest.mark.parametrize("name", RENDER)
+@pytest.mark.parametrize("impl", [1, 0])
+def test_render_matches_reference(name, impl):
+    g = load_golden("render_" + name)
+    f = _field_from_golden(g, impl)
+    action = _t(g["action"]).requires_grad_(True)
+    img, actual, refl = f.render(_t(g["sun"]), action, _t(g["ideal"]), monitor=True)
+    assert img.shape == g["img"].shape and actual.shape == g["actual"].shape and refl.shape == g["refl"].shape
+    np.testing.assert_allclose(img.detach().cpu().numpy(), g["img"], **IMG_TOL)
+    np.testing.assert_allclose(actual.detach().cpu().numpy(), g["actual"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(refl.detach().cpu().numpy(), g["refl"], rtol=1e-5, atol=1e-6)
+    gi, = torch.autograd.grad((img * _t(g["w_img"])).sum(), action, retain_graph=True)
+    assert rel_err(gi.cpu().numpy(), g["grad_img_only"]) < GRAD_TOL
+    loss = (img * _t(g["w_img"])).sum() + (actual * _t(g["w_act"])).sum() + (refl * _t(g["w_ref"])).sum()
+    ga, = torch.autograd.grad(loss, action)
+    assert rel_err(ga.cpu().numpy(), g["grad_all"]) < GRAD_TOL
+    # calculate_ideal_normals (newenv_rl_test_multi_error.py:256-278)
+    np.testing.assert_allclose(f.calculate_ideal_normals(_t(g["sun"])).cpu().numpy(), g["ideal"], rtol=1e-5, atol=1e-6)
+
+
+def test_render_return_contract():
+    g = load_golden("render_single")
+    f = _field_from_golden(g, 0)
+    out = f.render(_t(g["sun"]), _t(g["action"]), _t(g["ideal"]))
+    assert len(out) == 2 and out[0].shape == (16, 16) and out[1].shape == (1, 5, 3)       # [probed] quirk, SURVEY 8a a11
+    out = f.render(_t(g["sun"]), _t(g["action"]), _t(g["ideal"]), monitor=True)
+    assert len(out) == 3 and out[2].shape == (5, 3)
+
+
+def _env_from_golden(g, **kw):
+    from doodle_b200 import HelioEnv
+    env = HelioEnv(heliostat_pos=_t(g["helio"]), targ_pos=_t(g["targ_pos"]), targ_area=tuple(float(x) for x in g["area"]),
+                   targ_norm=_t(g["targ_norm"]), sigma_scale=float(g["sigma_scale"]), error_scale_mrad=float(g["err_mrad"]),
+                   initial_action_noise=0.0, resolution=int(g["R"]), batch_size=int(g["B"]), device="cuda:0",
+                   use_error_mask=bool(g["use_error_mask"]), exponential_risk=bool(g["exponential_risk"]), **kw)
+    env.set_sun_pos(_t(g["sun_pos"]))
+    env.noisy_field.batch_error_angles_mrad = _t(g["errs"])
+    env.noisy_field.error_angles_mrad = _t(g["err_single"])
+    return env
+
+
+@pytest.mark.parametrize("name", ENV)
+@pytest.mark.parametrize("cache", [False, True])
+def test_env_step_matches_reference(name, cache):
+    g = load_golden("env_" + name)
+    env = _env_from_golden(g, cache_target=cache)
+    B, R = int(g["B"]), int(g["R"])
+    # set_sun_pos products (test_environment.py:359-370)
+    np.testing.assert_allclose(env.distance_maps.cpu().numpy(), g["distance_maps"], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(float(env.ref_max), float(g["ref_max"]), rtol=1e-4)
+    for rep in range(2 if cache else 1):      # second pass exercises the cached target
+        action = _t(g["action"]).requires_grad_(True)
+        obs, metrics, monitor = env.step(action)
+        np.testing.assert_allclose(obs["img"].detach().cpu().numpy(), g["step_img"], **IMG_TOL)
+        np.testing.assert_allclose(obs["aux"].detach().cpu().numpy(), g["step_aux"], rtol=1e-6)
+        for k in ("mse", "dist", "bound", "alignment_loss"):
+            np.testing.assert_allclose(float(metrics[k]), float(g["metric_" + k]), rtol=2e-4, err_msg=k)
+        for k in ("normals", "reflected_rays", "ideal_normals", "all_bounds", "mae_image", "alignment_errors"):
+            ref = g["monitor_" + k]
+            got = monitor[k].detach().cpu().numpy()
+            assert got.shape == ref.shape, k
+            np.testing.assert_allclose(got, ref, rtol=2e-4, atol=1e-3 if k == "alignment_errors" else 1e-5, err_msg=k)
+        for k in ("mse", "dist", "bound", "alignment_loss"):
+            gr, = torch.autograd.grad(metrics[k], action, retain_graph=True, allow_unused=True)
+            assert rel_err(gr.cpu().numpy(), g["grad_" + k]) < GRAD_TOL, k
+
+
+def test_env_reset_matches_reference():
+    g = load_golden("env_readme")
+    env = _env_from_golden(g)
+    env.new_errors_every_reset = False
+    # HelioEnv never forwards initial_action_noise: the field default 0.01 applies; pin the draw
+    env.noisy_field.init_actions = lambda sun: setattr(env.noisy_field, "initial_action", _t(g["reset_action"]))
+    obs = env.reset()
+    np.testing.assert_allclose(obs["img"].cpu().numpy(), g["reset_img"], **IMG_TOL)
+    np.testing.assert_allclose(obs["aux"].cpu().numpy(), g["reset_aux"], rtol=1e-6)
+    np.testing.assert_allclose(env.ideal_normals.cpu().numpy(), g["ideal"], rtol=1e-5, atol=1e-6)
+
+
+# ---------------------------------------------------------------------------------------------
+# seeded random cases against the oracle, sizes the oracle finishes in seconds
+# ---------------------------------------------------------------------------------------------
+CASES = [
+    dict(N=50, R=128, B=25, sigma=0.1, spread=10.0, off=0.0, err=90.0),     # BASELINE configs[0]/[1] (README shape)
+    dict(N=50, R=128, B=6, sigma=0.01, spread=10.0, off=80.0, err=90.0),    # trainer geometry
+    dict(N=37, R=100, B=3, sigma=0.05, spread=10.0, off=20.0, err=30.0),    # HelioField default resolution, R % 8 != 0
+    dict(N=5, R=33, B=2, sigma=0.1, spread=10.0, off=0.0, err=10.0),        # odd R: scalar load/store paths
+    dict(N=130, R=64, B=9, sigma=0.02, spread=30.0, off=60.0, err=5.0),     # N not a multiple of any chunk
+    dict(N=1, R=16, B=1, sigma=0.1, spread=10.0, off=0.0, err=0.0),         # degenerate sizes
+    dict(N=300, R=256, B=2, sigma=0.01, spread=10.0, off=80.0, err=90.0),   # 256x256 receiver (BASELINE configs[3] resolution)
+]
+
+
+def _random_case(c, seed=0):
+    rng = np.random.default_rng(seed)
+    N, B = c["N"], c["B"]
+    helio = np.concatenate([rng.random((N, 2)) * c["spread"] + c["off"], np.zeros((N, 1))], 1).astype(np.float32)
+    d = np.array([[0.5, 0.5, 0.7071]]) + 0.02 * rng.standard_normal((B, 3))
+    sun = (d / np.linalg.norm(d, axis=1, keepdims=True) * 14142.0).astype(np.float32)
+    ideal = orc.calculate_ideal_normals(sun, helio, [0., -5., 0.])
+    act = (ideal + 0.01 * rng.standard_normal(ideal.shape)).astype(np.float32)
+    errs = (rng.standard_normal((B, N, 2)) * c["err"]).astype(np.float32)
+    w_img = rng.standard_normal((B, c["R"], c["R"])).astype(np.float32)
+    return helio, sun, act, errs, w_img
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: f"N{c['N']}_R{c['R']}_B{c['B']}")
+@pytest.mark.parametrize("impl", [1, 0])
+def test_render_matches_oracle(case, impl):
+    from doodle_b200 import HelioField
+    helio, sun, act, errs, w_img = _random_case(case)
+    R, B, N = case["R"], case["B"], case["N"]
+    (img_o, actual_o, refl_o), ctx = orc.render_forward(sun, act, errs, helio, [0., -5., 0.], [0., 1., 0.], (15., 15.), R,
+                                                        case["sigma"], keep=True)
+    grad_o = orc.render_backward(ctx, g_img=w_img)
+    (img64, _, _), ctx64 = orc.render_forward(sun, act, errs, helio, [0., -5., 0.], [0., 1., 0.], (15., 15.), R,
+                                              case["sigma"], dtype=np.float64, keep=True)
+    grad64 = orc.render_backward(ctx64, g_img=w_img)
+    f = HelioField(_t(helio), _t(np.float32([0., -5., 0.])), (15., 15.), _t(np.float32([0., 1., 0.])),
+                   error_scale_mrad=case["err"], sigma_scale=case["sigma"], resolution=R, device="cuda:0", max_batch_size=max(B, 2))
+    f.batch_error_angles_mrad = _t(errs)
+    f.error_angles_mrad = _t(errs[0])
+    f.splat_impl = impl
+    action = _t(act).requires_grad_(True)
+    img, actual, refl = f.render(_t(sun) if B > 1 else _t(sun[0]), action, None, monitor=True)
+    img = img.view(B, R, R)
+    got = img.detach().cpu().numpy()
+    # fp32 oracle first; where the two fp32 results disagree near tolerance the fp64 oracle decides
+    try:
+        np.testing.assert_allclose(got, img_o, **IMG_TOL)
+    except AssertionError:
+        np.testing.assert_allclose(got, img64, **IMG_TOL)
+    np.testing.assert_allclose(actual.detach().cpu().numpy().reshape(B, N, 3), actual_o, rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(refl.detach().cpu().numpy(), refl_o, rtol=1e-5, atol=1e-6)
+    gr, = torch.autograd.grad((img * _t(w_img)).sum(), action)
+    gr = gr.cpu().numpy().reshape(B, N, 3)
+    assert min(rel_err(gr, grad_o), rel_err(gr, grad64)) < GRAD_TOL
+
+
+def test_impls_agree():
+    """SIMT and AUTO (tcgen05 where supported) give the same images and moments."""
+    from doodle_b200 import HelioField
+    case = dict(N=256, R=256, B=3, sigma=0.01, spread=10.0, off=80.0, err=90.0)
+    helio, sun, act, errs, w_img = _random_case(case, seed=3)
+    outs = []
+    for impl in (1, 0):
+        f = HelioField(_t(helio), _t(np.float32([0., -5., 0.])), (15., 15.), _t(np.float32([0., 1., 0.])),
+                       error_scale_mrad=90.0, sigma_scale=0.01, resolution=256, device="cuda:0", max_batch_size=3)
+        f.batch_error_angles_mrad = _t(errs)
+        f.splat_impl = impl
+        a = _t(act).requires_grad_(True)
+        img, _ = f.render(_t(sun), a, None)
+        g, = torch.autograd.grad((img * _t(w_img)).sum(), a)
+        outs.append((img.detach().cpu().numpy(), g.cpu().numpy()))
+    np.testing.assert_allclose(outs[1][0], outs[0][0], **IMG_TOL)
+    assert rel_err(outs[1][1], outs[0][1]) < GRAD_TOL
+
+
+# ---------------------------------------------------------------------------------------------
+# size-independent properties at the full BASELINE resolution / heliostat count
+# ---------------------------------------------------------------------------------------------
+def test_full_size_properties():
+    """N=2000, R=256 (BASELINE configs[3] per-sun shape; B kept small so the test is quick):
+    (1) linearity over heliostats: img(all) == img(first half) + img(second half);
+    (2) error-free field aimed with ideal normals puts every ray on the target centre: the image equals the
+        analytic sum_n exp(-(x_i^2 + y_j^2)/(2 sigma_n^2)) (SURVEY 8c KAT), alignment loss is the acos floor
+        0.3453 mrad, boundary loss 0;
+    (3) adjoint identity: <g, J v> from a finite step along v equals <J^T g, v> from backward."""
+    from doodle_b200 import HelioField
+    torch.manual_seed(1)
+    dev = "cuda:0"
+    N, R, B = 2000, 256, 4
+    helio = torch.rand(N, 3, device=dev) * 10 + 80
+    helio[:, 2] = 0
+    tp, tn = torch.tensor([0., -5., 0.], device=dev), torch.tensor([0., 1., 0.], device=dev)
+    mk = lambda h, err: HelioField(h, tp, (15., 15.), tn, error_scale_mrad=err, sigma_scale=0.01, resolution=R, device=dev,
+                                   max_batch_size=B)
+    d = torch.nn.functional.normalize(torch.tensor([[0.5, 0.5, 0.7071]], device=dev) + 0.02 * torch.randn(B, 3, device=dev), dim=1)
+    sun = d * 14142.0
+    full = mk(helio, 90.0)
+    ideal = full.calculate_ideal_normals(sun)
+    act = ideal + 0.01 * torch.randn_like(ideal)
+    img_all, _ = full.render(sun, act, ideal)
+    halves = []
+    for sl in (slice(0, N // 2), slice(N // 2, N)):
+        f = mk(helio[sl], 90.0)
+        f.batch_error_angles_mrad = full.batch_error_angles_mrad[:, sl].contiguous()
+        halves.append(f.render(sun, act[:, sl].contiguous(), None)[0])
+    torch.testing.assert_close(img_all, halves[0] + halves[1], rtol=1e-4, atol=1e-5)
+
+    clean = mk(helio, 0.0)
+    out = clean._render_full(sun, ideal, want_aux=True)
+    xs = torch.linspace(-7.5, 7.5, R, device=dev, dtype=torch.float64)
+    sig = 0.01 * (tp[None].double() - helio.double()).norm(dim=1)                    # [N]
+    gx = torch.exp(-xs[None] ** 2 / (2 * sig[:, None] ** 2))                         # [N,R]
+    analytic = torch.einsum("ni,nj->ij", gx, gx)
+    for b in range(B):
+        torch.testing.assert_close(out.img[b].double(), analytic, rtol=2e-4, atol=1e-4)
+    assert abs(float(out.sums[1]) / (B * N) - 0.3453) < 2e-3
+    assert float(out.sums[0]) == 0.0
+
+    a = act.clone().requires_grad_(True)
+    img, _ = full.render(sun, a, None)
+    g = torch.randn_like(img)
+    jt_g, = torch.autograd.grad((img * g).sum(), a)
+    v = torch.randn_like(a)
+    v = v / v.norm()
+    eps = 1e-4
+    with torch.no_grad():
+        ip, _ = full.render(sun, act + eps * v, None)
+        im, _ = full.render(sun, act - eps * v, None)
+    lhs = float(((ip.double() - im.double()) / (2 * eps) * g.double()).sum())
+    rhs = float((jt_g.double() * v.double()).sum())
+    assert abs(lhs - rhs) <= 2e-2 * max(abs(lhs), abs(rhs), 1.0), (lhs, rhs)
+
+
+def test_behaviour_checks_from_reference_sanity_script():
+    """newenv/sanity_check_multi_error.py:172-247: duplicated suns give distinct images (per-sun errors),
+    reset_errors() changes the image, a shifted sun changes the image."""
+    from doodle_b200 import HelioField
+    torch.manual_seed(5)
+    dev = "cuda:0"
+    helio = torch.rand(5, 3, device=dev) * 10
+    helio[:, 2] = 0
+    f = HelioField(helio, torch.tensor([0., -5., 0.]), (15., 15.), torch.tensor([0., 1., 0.]), error_scale_mrad=80.0,
+                   sigma_scale=0.1, resolution=64, device=dev, max_batch_size=4)
+    sun = torch.tensor([[700., 700., 700.]] * 2, device=dev)
+    ideal = f.calculate_ideal_normals(sun)
+    img, _ = f.render(sun, ideal.flatten(1), ideal)
+    assert float((img[0] - img[1]).abs().max()) > 1e-6
+    img_again, _ = f.render(sun, ideal.flatten(1), ideal)
+    assert torch.equal(img, img_again)                         # deterministic until reset_errors
+    f.reset_errors()
+    img2, _ = f.render(sun, ideal.flatten(1), ideal)
+    assert float((img - img2).abs().max()) > 1e-6
+    sun3 = sun + torch.tensor([50., 0., 0.], device=dev)
+    img3, _ = f.render(sun3, ideal.flatten(1), ideal)
+    assert float((img3 - img2).abs().max()) > 1e-6
+    # B > max_batch_size: fresh errors every call (newenv_rl_test_multi_error.py:352-353)
+    sun8 = sun[:1].repeat(8, 1)
+    id8 = f.calculate_ideal_normals(sun8)
+    a, _ = f.render(sun8, id8.flatten(1), id8)
+    b, _ = f.render(sun8, id8.flatten(1), id8)
+    assert float((a - b).abs().max()) > 1e-6
+
+
+def test_alignment_descent_through_step():
+    """env_sanity_check.py:57-84: Adam on free normals through env.step drives alignment_loss down."""
+    from doodle_b200 import HelioEnv
+    torch.manual_seed(666)
+    dev = "cuda:0"
+    N, B = 1, 64
+    helio = torch.rand(N, 3, device=dev) * 10 + 1500
+    helio[:, 2] = 0
+    env = HelioEnv(heliostat_pos=helio, targ_pos=torch.tensor([0., -5., 0.], device=dev), targ_area=(15., 15.),
+                   targ_norm=torch.tensor([0., 1., 0.], device=dev), sigma_scale=0.01, error_scale_mrad=2.0,
+                   initial_action_noise=0.0, resolution=64, batch_size=B, device=dev, new_errors_every_reset=False)
+    env.seed(666)
+    env.reset()
+    raw = torch.nn.Parameter(torch.randn(B, N, 3, device=dev))
+    opt = torch.optim.Adam([raw], lr=0.05)
+    first = last = None
+    for _ in range(60):
+        opt.zero_grad(set_to_none=True)
+        _, loss_dict, _ = env.step(torch.nn.functional.normalize(raw, dim=2))
+        loss = loss_dict["alignment_loss"]
+        loss.backward()
+        opt.step()
+        first = float(loss) if first is None else first
+        last = float(loss)
+    assert last < 0.5 * first, (first, last)
+
+
+def test_abi_errors():
+    """Error behaviour of the C ABI: bad arguments return HELIO_E_BADARG with a message, no exception crosses."""
+    import ctypes as C
+    from doodle_b200 import _lib
+    lib = _lib.load()
+    assert lib.helio_device_ok() == 1
+    rc = lib.helio_splat_fwd(None, 1, 1, 8, 1.0, 1.0, None, 0, None)
+    assert rc == -1 and b"null" in lib.helio_last_error()
+    x = torch.zeros(4, device="cuda:0")
+    rc = lib.helio_splat_fwd(C.c_void_p(x.data_ptr()), 0, 1, 8, 1.0, 1.0, C.c_void_p(x.data_ptr()), 0, None)
+    assert rc == -1
+    rc = lib.helio_splat_fwd(C.c_void_p(x.data_ptr()), 1, 1, 8, 1.0, 1.0, C.c_void_p(x.data_ptr()), 7, None)
+    assert rc == -1 and b"impl" in lib.helio_last_error()
+    with pytest.raises(_lib.HelioLibError):
+        _lib.check(rc, "helio_splat_fwd")
