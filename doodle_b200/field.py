@@ -62,7 +62,8 @@ class HelioField:
             self.plane_v = v / v.norm().clamp_min(1e-9)
 
         self.initial_action = None
-        self.splat_impl = SPLAT_AUTO
+        self.splat_impl = SPLAT_AUTO        # forward splat: SPLAT_AUTO | SPLAT_SIMT | SPLAT_TC
+        self.splat_impl_bwd = None          # backward splat; None = same selector as forward
         self._scene = None
         self._bnd = None
         self._workspace = {}
@@ -170,7 +171,8 @@ class HelioField:
         ws = self._geom_workspace(B) if want_aux else None
         params, actual, refl, ideal, bounds, angles, sums = GeomFn.apply(
             normals, _cf(sun), errs, self.heliostat_positions, self.scene(), ws, want_aux)
-        img = SplatFn.apply(params, self.resolution, float(self.target_width), float(self.target_height), self.splat_impl)
+        img = SplatFn.apply(params, self.resolution, float(self.target_width), float(self.target_height), self.splat_impl,
+                            self.splat_impl if self.splat_impl_bwd is None else self.splat_impl_bwd)
         return SimpleNamespace(img=img, actual=actual, refl=refl, ideal=ideal, bounds=bounds, angles=angles, sums=sums,
                                normals=normals)
 

@@ -145,7 +145,7 @@ class SplatFn(torch.autograd.Function):
     """K2/K3: params -> img[B,R,R]; backward returns the moments tensor in the slot of params."""
 
     @staticmethod
-    def forward(ctx, params, R: int, width: float, height: float, impl: int):
+    def forward(ctx, params, R: int, width: float, height: float, impl: int, impl_bwd: int):
         lib = _lib.load()
         B, N = params.shape[0], params.shape[1]
         img = torch.empty(B, R, R, dtype=torch.float32, device=params.device)
@@ -153,7 +153,7 @@ class SplatFn(torch.autograd.Function):
             rc = lib.helio_splat_fwd(_ptr(params), B, N, R, width, height, _ptr(img), impl, _stream())
         _lib.check(rc, "helio_splat_fwd")
         ctx.save_for_backward(params)
-        ctx.cfg = (R, width, height, impl)
+        ctx.cfg = (R, width, height, impl_bwd)
         return img
 
     @staticmethod
@@ -167,7 +167,7 @@ class SplatFn(torch.autograd.Function):
         with _Call("splat_bwd", params.device):
             rc = lib.helio_splat_bwd(_ptr(params), _ptr(g_img), B, N, R, width, height, _ptr(moments), impl, _stream())
         _lib.check(rc, "helio_splat_bwd")
-        return moments, None, None, None, None
+        return moments, None, None, None, None, None
 
 
 def image_max(target: torch.Tensor) -> torch.Tensor:
