@@ -1,4 +1,5 @@
 // extern "C" entry points of libhelio_sm100.so (see include/helio_b200.h for the contract).
+#include <cstdlib>
 #include <mutex>
 
 #include "geom.cuh"
@@ -44,6 +45,17 @@ int require_device(const DeviceInfo** out) {
     }
     *out = d;
     return 0;
+}
+
+// HELIO_TC_PAIR = 1 forces single-CTA tcgen05 kernels, 2 forces CTA pairs (cta_group::2); default 0 = auto.
+// Debug / A-B switch only; read once.
+int tc_pair_mode() {
+    static const int mode = []() {
+        const char* e = std::getenv("HELIO_TC_PAIR");
+        const int v = e ? std::atoi(e) : 0;
+        return (v == 1 || v == 2) ? v : 0;
+    }();
+    return mode;
 }
 
 inline unsigned geom_blocks(int B, int N) { return (unsigned)(((long long)B * N + kGeomThreads - 1) / kGeomThreads); }
@@ -110,7 +122,7 @@ HELIO_API int helio_splat_fwd(const float* params, int B, int N, int R, float wi
     if (impl == HELIO_SPLAT_TC && !tc_ok)
         return set_error(HELIO_E_BADARG, "tcgen05 splat forward does not support this shape%s%s");
     if (impl == HELIO_SPLAT_TC || (impl == HELIO_SPLAT_AUTO && tc_ok && splat_tc_fwd_preferred(B, N, R))) {
-        HELIO_CUDA_OK(splat_tc_fwd(params, img, B, N, R, width, height, d->sms, (cudaStream_t)stream));
+        HELIO_CUDA_OK(splat_tc_fwd(params, img, B, N, R, width, height, d->sms, (cudaStream_t)stream, tc_pair_mode()));
     } else {
         HELIO_CUDA_OK(splat_fwd_simt(params, img, B, N, R, width, height, d->sms, (cudaStream_t)stream));
     }
@@ -128,7 +140,7 @@ HELIO_API int helio_splat_bwd(const float* params, const float* g_img, int B, in
     if (impl == HELIO_SPLAT_TC && !tc_ok)
         return set_error(HELIO_E_BADARG, "tcgen05 splat backward does not support this shape%s%s");
     if (impl == HELIO_SPLAT_TC || (impl == HELIO_SPLAT_AUTO && tc_ok && splat_tc_bwd_preferred(B, N, R))) {
-        HELIO_CUDA_OK(splat_tc_bwd(params, g_img, moments, B, N, R, width, height, d->sms, (cudaStream_t)stream));
+        HELIO_CUDA_OK(splat_tc_bwd(params, g_img, moments, B, N, R, width, height, d->sms, (cudaStream_t)stream, tc_pair_mode()));
     } else {
         HELIO_CUDA_OK(splat_bwd_simt(params, g_img, moments, B, N, R, width, height, d->sms, (cudaStream_t)stream));
     }

@@ -14,12 +14,17 @@
 //                    (backward) a second producer group stages the image-gradient tile of g,
 //                    split the same way (transposed on the fly for the U product);
 //   MMA warp       : one elected thread issues, per 32-deep K stage, 4 K-steps x {hi*hi, hi*lo,
-//                    lo*hi} tcgen05.mma kind::tf32 into a 128 x NT fp32 accumulator in TMEM;
-//                    two accumulators ping-pong so the epilogue overlaps the next tile;
+//                    lo*hi} tcgen05.mma kind::tf32 into a fp32 accumulator in TMEM; two
+//                    accumulators ping-pong so the epilogue overlaps the next tile;
 //   epilogue warps : tcgen05.ld the accumulator; forward stores image rows, backward folds the
 //                    recomputed Gaussian weights into the per-heliostat moments.
 // Pipelines: smem full/empty per stage (producers <-> MMA), TMEM full/empty per accumulator
 // (MMA <-> epilogue), static round-robin tile schedule.
+//
+// CG = 2 runs the same kernels on CTA pairs (cta_group::2, cluster of two SMs): the pair shares one
+// 256-row accumulator tile (128 TMEM lanes per CTA), each CTA generates its 128 A rows and only its
+// half of the B rows, and the leader's MMA reads both shared memories.  That cuts the operand bytes
+// each SM writes and the tensor core reads per MMA by a third and leaves room for a third stage.
 //
 // Accuracy: hi*hi + hi*lo + lo*hi with fp32 accumulation drops only lo*lo (~2^-22 relative) and
 // the truncation of lo (~2^-21): fp32-class results from the tensor pipe.
@@ -31,84 +36,195 @@ namespace helio {
 
 constexpr int kTcMaxR = 1024;  // coordinate tables live in shared memory
 
-// ================================================================================================
-// forward
-// ================================================================================================
-template <int NT>
-struct SplatFwdTc {
-    static constexpr int kNT = NT;                       // UMMA N (image columns per tile)
-    static constexpr int kM = 128;                       // UMMA M (image rows per tile)
-    static constexpr int kKC = 32;                       // heliostats per stage (one 128-byte swizzle row)
-    static constexpr int kStages = (NT == 256) ? 2 : 3;
-    static constexpr int kProducerWarps = (kM + NT) / 32;
-    static constexpr int kMmaWarp = kProducerWarps;
-    static constexpr int kEpiWarp0 = kProducerWarps + 1;
-    static constexpr int kThreads = (kProducerWarps + 1 + 4) * 32;
+// ------------------------------------------------------------------------------------------------
+// pieces shared by both kernels
+// ------------------------------------------------------------------------------------------------
+template <int NT, int CG, int BROWS>
+struct SplatTcLayout {
+    static constexpr int kNT = NT;                       // UMMA N (accumulator columns)
+    static constexpr int kM = 128;                       // A rows per CTA = TMEM lanes
+    static constexpr int kBRows = BROWS;                 // B operand rows produced by each CTA (NT / CG)
+    static constexpr int kKC = 32;                       // K per stage (one 128-byte swizzle row of tf32)
+    static constexpr int kAWarps = kM / 32;
+    static constexpr int kBWarps = kBRows / 32;
+    static constexpr int kMmaWarp = kAWarps + kBWarps;
+    static constexpr int kEpiWarp0 = kMmaWarp + 1;
+    static constexpr int kThreads = (kEpiWarp0 + 4) * 32;
     static constexpr int kABytes = kM * 128;             // one of {hi, lo}
-    static constexpr int kBBytes = NT * 128;
+    static constexpr int kBBytes = kBRows * 128;
     static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
     static constexpr int kTmemCols = 2 * NT;             // two accumulators
     static constexpr int kTableBytes = 2 * kTcMaxR * 4;
-    static constexpr int kSmemBytes = kStages * kStageBytes + kTableBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
-    static_assert(kTmemCols <= 512 && (kTmemCols & (kTmemCols - 1)) == 0, "TMEM columns: power of two <= 512");
-    static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+    static constexpr int kFixedBytes = kTableBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
+    static constexpr int kFit = (227 * 1024 - kFixedBytes) / kStageBytes;
+    static constexpr int kStages = kFit > 4 ? 4 : kFit;
+    static constexpr int kSmemBytes = kStages * kStageBytes + kFixedBytes;
+    static constexpr int kFullCount = (kAWarps + kBWarps) * CG;   // one arrival per producer warp of the pair
+    static constexpr int kTEmptyCount = 4 * CG;                   // one arrival per epilogue warp of the pair
+    static_assert(CG == 1 || CG == 2, "CTA group size");
+    static_assert(BROWS * CG == NT, "each CTA of the group stages NT / CG rows of B");
+    static_assert(kTmemCols <= 512 && (kTmemCols & (kTmemCols - 1)) == 0 && kTmemCols >= 32, "TMEM columns");
+    static_assert(kStages >= 2 && kSmemBytes <= 227 * 1024, "shared memory budget");
 };
+
+// shared-memory carve-up + one-time setup common to the forward and backward kernels
+template <class C, int CG>
+struct SplatTcCtx {
+    uint8_t* smem;        // operand stages (1024-byte aligned)
+    float *sX, *sY;       // pixel-centre tables
+    uint64_t *full, *empty, *tfull, *tempty;
+    uint32_t tmem_base;
+    uint32_t rank;        // CTA rank inside the pair (0 when CG == 1)
+
+    __device__ __forceinline__ void setup(uint8_t* smem_raw, int R, const Axis& ax, const Axis& ay) {
+        smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+        sX = reinterpret_cast<float*>(smem + C::kStages * C::kStageBytes);
+        sY = sX + kTcMaxR;
+        uint64_t* bars = reinterpret_cast<uint64_t*>(sY + kTcMaxR);
+        full = bars;                       // [kStages]  producers -> MMA   (leader's copy is the live one)
+        empty = bars + C::kStages;         // [kStages]  MMA -> producers
+        tfull = bars + 2 * C::kStages;     // [2]        MMA -> epilogue
+        tempty = tfull + 2;                // [2]        epilogue -> MMA   (leader's copy is the live one)
+        uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+        rank = CG == 2 ? tc::cluster_ctarank() : 0u;
+        const int warp = threadIdx.x >> 5;
+
+        // pixel-centre tables, padded with 0 (rows/columns >= R are computed but never stored)
+        for (int i = threadIdx.x; i < kTcMaxR; i += C::kThreads) {
+            sX[i] = i < R ? axis_at(ax, i) : 0.f;
+            sY[i] = i < R ? axis_at(ay, i) : 0.f;
+        }
+        if (threadIdx.x == 0) {
+            for (int s = 0; s < C::kStages; ++s) {
+                tc::mbar_init(&full[s], C::kFullCount);
+                tc::mbar_init(&empty[s], 1);
+            }
+            for (int a = 0; a < 2; ++a) {
+                tc::mbar_init(&tfull[a], 1);
+                tc::mbar_init(&tempty[a], C::kTEmptyCount);
+            }
+            tc::mbar_fence_init();
+        }
+        if (warp == C::kMmaWarp) {
+            if constexpr (CG == 2) {
+                tc::tmem_alloc_2cta(tmem_slot, C::kTmemCols);
+                tc::tmem_relinquish_2cta();
+            } else {
+                tc::tmem_alloc(tmem_slot, C::kTmemCols);
+                tc::tmem_relinquish();
+            }
+        }
+        tc::tc_fence_before();
+        __syncthreads();
+        if constexpr (CG == 2) tc::cluster_sync();   // peer barriers initialised before any remote arrive
+        tc::tc_fence_after();
+        tmem_base = *tmem_slot;
+    }
+
+    __device__ __forceinline__ void teardown() {
+        tc::tc_fence_before();
+        __syncthreads();
+        if constexpr (CG == 2) tc::cluster_sync();   // no CTA leaves while its peer may still signal it
+        if ((threadIdx.x >> 5) == C::kMmaWarp) {
+            tc::tc_fence_after();
+            if constexpr (CG == 2) tc::tmem_dealloc_2cta(tmem_base, C::kTmemCols);
+            else tc::tmem_dealloc(tmem_base, C::kTmemCols);
+        }
+    }
+
+    // producer warp: stage s written (all lanes) -> one arrival on the group's full barrier
+    __device__ __forceinline__ void producer_commit(int s) const {
+        tc::fence_proxy_async_smem();
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) {
+            if constexpr (CG == 2) tc::mbar_arrive_remote(&full[s], 0);
+            else tc::mbar_arrive(&full[s]);
+        }
+    }
+    // producer warp: wait until the MMAs that read stage s have retired
+    __device__ __forceinline__ void producer_acquire(int s, uint32_t ph) const {
+        if ((threadIdx.x & 31) == 0) tc::mbar_wait(&empty[s], ph ^ 1);
+        __syncwarp();
+    }
+    // epilogue warp: accumulator drained -> one arrival on the group's tempty barrier
+    __device__ __forceinline__ void epilogue_release(int acc) const {
+        tc::tc_fence_before();
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) {
+            if constexpr (CG == 2) tc::mbar_arrive_remote(&tempty[acc], 0);
+            else tc::mbar_arrive(&tempty[acc]);
+        }
+    }
+    // MMA thread: one stage = 4 K-steps x {hi*hi, hi*lo, lo*hi}; `first` clears the accumulator
+    __device__ __forceinline__ void issue_stage(int s, uint32_t d_tmem, bool first, bool last, int acc) const {
+        constexpr uint32_t idesc = tc::make_idesc_tf32(C::kM * CG, C::kNT);
+        const uint32_t sa = tc::smem_u32(smem + s * C::kStageBytes);
+        const uint64_t a_hi = tc::make_desc_k_sw128(sa);
+        const uint64_t a_lo = tc::make_desc_k_sw128(sa + C::kABytes);
+        const uint64_t b_hi = tc::make_desc_k_sw128(sa + 2 * C::kABytes);
+        const uint64_t b_lo = tc::make_desc_k_sw128(sa + 2 * C::kABytes + C::kBBytes);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint64_t ko = (uint64_t)(k * 32 >> 4);   // +32 bytes per K step of 8 tf32
+            if constexpr (CG == 2) {
+                tc::mma_tf32_ss_2cta(d_tmem, a_hi + ko, b_hi + ko, idesc, !(first && k == 0));
+                tc::mma_tf32_ss_2cta(d_tmem, a_hi + ko, b_lo + ko, idesc, 1);
+                tc::mma_tf32_ss_2cta(d_tmem, a_lo + ko, b_hi + ko, idesc, 1);
+            } else {
+                tc::mma_tf32_ss(d_tmem, a_hi + ko, b_hi + ko, idesc, !(first && k == 0));
+                tc::mma_tf32_ss(d_tmem, a_hi + ko, b_lo + ko, idesc, 1);
+                tc::mma_tf32_ss(d_tmem, a_lo + ko, b_hi + ko, idesc, 1);
+            }
+        }
+        if constexpr (CG == 2) {
+            tc::mma_commit_2cta(&empty[s], 3);               // stage reusable in both CTAs when these MMAs retire
+            if (last) tc::mma_commit_2cta(&tfull[acc], 3);   // accumulator complete in both CTAs
+        } else {
+            tc::mma_commit(&empty[s]);
+            if (last) tc::mma_commit(&tfull[acc]);
+        }
+    }
+    __device__ __forceinline__ void mma_wait_full(int s, uint32_t ph) const {
+        if constexpr (CG == 2) tc::mbar_wait_cluster(&full[s], ph);
+        else tc::mbar_wait(&full[s], ph);
+        tc::tc_fence_after();
+    }
+    __device__ __forceinline__ void mma_wait_tempty(int acc, uint32_t aph) const {
+        if constexpr (CG == 2) tc::mbar_wait_cluster(&tempty[acc], aph ^ 1);
+        else tc::mbar_wait(&tempty[acc], aph ^ 1);
+        tc::tc_fence_after();
+    }
+};
+
+// ================================================================================================
+// forward
+// ================================================================================================
+template <int NT, int CG>
+using SplatFwdTc = SplatTcLayout<NT, CG, NT / CG>;
 
 // Producer mapping: a warp owns 32 operand rows (image rows for A, image columns for B) and its
 // lanes own the 32 heliostats of the stage, so the footprint parameters sit in registers (one
 // coalesced 512-byte load per warp and stage, prefetched one stage ahead) and every store is one
 // conflict-free 128-byte row of the swizzled tile.
-template <int NT>
-__global__ void __launch_bounds__(SplatFwdTc<NT>::kThreads, 1)
+template <int NT, int CG>
+__global__ void __launch_bounds__(SplatFwdTc<NT, CG>::kThreads, 1)
 splat_fwd_tc_kernel(const float4* __restrict__ params, float* __restrict__ img, int N, int R, Axis ax, Axis ay,
                     int tiles_i, int tiles_j, int num_tiles) {
-    using C = SplatFwdTc<NT>;
+    using C = SplatFwdTc<NT, CG>;
     extern __shared__ uint8_t smem_raw[];
-    // 1024-byte aligned operand stages, then coordinate tables, then barriers
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    float* sX = reinterpret_cast<float*>(smem + C::kStages * C::kStageBytes);
-    float* sY = sX + kTcMaxR;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sY + kTcMaxR);
-    uint64_t* full = bars;                       // [kStages]  producers -> MMA
-    uint64_t* empty = bars + C::kStages;         // [kStages]  MMA -> producers
-    uint64_t* tfull = bars + 2 * C::kStages;     // [2]        MMA -> epilogue
-    uint64_t* tempty = tfull + 2;                // [2]        epilogue -> MMA
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    SplatTcCtx<C, CG> cx;
+    cx.setup(smem_raw, R, ax, ay);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-    // pixel-centre tables, padded with 0 (rows/columns >= R are computed but never stored)
-    for (int i = threadIdx.x; i < kTcMaxR; i += C::kThreads) {
-        sX[i] = i < R ? axis_at(ax, i) : 0.f;
-        sY[i] = i < R ? axis_at(ay, i) : 0.f;
-    }
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < C::kStages; ++s) {
-            tc::mbar_init(&full[s], C::kProducerWarps);
-            tc::mbar_init(&empty[s], 1);
-        }
-        for (int a = 0; a < 2; ++a) {
-            tc::mbar_init(&tfull[a], 1);
-            tc::mbar_init(&tempty[a], 128);
-        }
-        tc::mbar_fence_init();
-    }
-    if (warp == C::kMmaWarp) {
-        tc::tmem_alloc(tmem_slot, C::kTmemCols);
-        tc::tmem_relinquish();
-    }
-    tc::tc_fence_before();
-    __syncthreads();
-    tc::tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
     const int nchunks = (N + C::kKC - 1) / C::kKC;
     const int tiles_per_img = tiles_i * tiles_j;
+    const int group = blockIdx.x / CG, ngroups = gridDim.x / CG;
+    constexpr int kTileM = C::kM * CG;
 
-    if (warp < C::kProducerWarps) {
+    if (warp < C::kMmaWarp) {
         // ================= producers =================
-        const bool isA = warp < C::kM / 32;
-        const int wrow = (isA ? warp : warp - C::kM / 32) * 32;          // first operand row of this warp
+        const bool isA = warp < C::kAWarps;
+        const int wrow = (isA ? warp : warp - C::kAWarps) * 32;          // first operand row of this warp (CTA-local)
         const uint32_t region = (isA ? 0u : 2u * C::kABytes) + (uint32_t)(wrow >> 3) * 1024u;
         const uint32_t lo_delta = isA ? C::kABytes : C::kBBytes;
         // byte offset of this lane's element inside a 128-byte row whose (row & 7) == c
@@ -116,10 +232,10 @@ splat_fwd_tc_kernel(const float4* __restrict__ params, float* __restrict__ img, 
 #pragma unroll
         for (int c = 0; c < 8; ++c) xoff[c] = ((((uint32_t)lane >> 2) ^ (uint32_t)c) << 4) + ((uint32_t)lane & 3u) * 4u;
         uint32_t it = 0;                             // global stage counter
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int tile = group; tile < num_tiles; tile += ngroups) {
             const int b = tile / tiles_per_img, t = tile % tiles_per_img;
-            const int g0 = (isA ? (t / tiles_j) * C::kM : (t % tiles_j) * NT) + wrow;
-            const float* tab = (isA ? sX : sY) + g0;
+            const int g0 = (isA ? (t / tiles_j) * kTileM + (int)cx.rank * C::kM : (t % tiles_j) * NT + (int)cx.rank * C::kBRows) + wrow;
+            const float* tab = (isA ? cx.sX : cx.sY) + g0;
             float xr[32];
 #pragma unroll
             for (int e = 0; e < 32; e += 4) {
@@ -137,10 +253,8 @@ splat_fwd_tc_kernel(const float4* __restrict__ params, float* __restrict__ img, 
                 const float nk2 = -p.z;
                 const float scale = have ? (isA ? p.w : 1.f) : 0.f;     // K padding: exact zeros
                 const int s = it % C::kStages;
-                const uint32_t ph = (it / C::kStages) & 1;
-                if (lane == 0) tc::mbar_wait(&empty[s], ph ^ 1);
-                __syncwarp();
-                uint8_t* base = smem + s * C::kStageBytes + region;
+                cx.producer_acquire(s, (it / C::kStages) & 1);
+                uint8_t* base = cx.smem + s * C::kStageBytes + region;
 #pragma unroll
                 for (int e = 0; e < 32; ++e) {
                     const float d = xr[e] - ctr;
@@ -151,59 +265,38 @@ splat_fwd_tc_kernel(const float4* __restrict__ params, float* __restrict__ img, 
                     *reinterpret_cast<float*>(dst) = hi;
                     *reinterpret_cast<float*>(dst + lo_delta) = lo;
                 }
-                tc::fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) tc::mbar_arrive(&full[s]);
+                cx.producer_commit(s);
             }
         }
     } else if (warp == C::kMmaWarp) {
-        // ================= MMA issuer =================
-        constexpr uint32_t idesc = tc::make_idesc_tf32(C::kM, NT);
-        uint32_t it = 0, tcount = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
-            const int acc = tcount & 1;
-            const uint32_t aph = (tcount >> 1) & 1;
-            tc::mbar_wait(&tempty[acc], aph ^ 1);
-            tc::tc_fence_after();
-            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * NT);
-            for (int c = 0; c < nchunks; ++c, ++it) {
-                const int s = it % C::kStages;
-                const uint32_t ph = (it / C::kStages) & 1;
-                tc::mbar_wait(&full[s], ph);
-                tc::tc_fence_after();
-                if (lane == 0) {
-                    const uint32_t sa = tc::smem_u32(smem + s * C::kStageBytes);
-                    const uint64_t a_hi = tc::make_desc_k_sw128(sa);
-                    const uint64_t a_lo = tc::make_desc_k_sw128(sa + C::kABytes);
-                    const uint64_t b_hi = tc::make_desc_k_sw128(sa + 2 * C::kABytes);
-                    const uint64_t b_lo = tc::make_desc_k_sw128(sa + 2 * C::kABytes + C::kBBytes);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const uint64_t ko = (uint64_t)(k * 32 >> 4);   // +32 bytes per K step of 8 tf32
-                        tc::mma_tf32_ss(d_tmem, a_hi + ko, b_hi + ko, idesc, (c | k) != 0);
-                        tc::mma_tf32_ss(d_tmem, a_hi + ko, b_lo + ko, idesc, 1);
-                        tc::mma_tf32_ss(d_tmem, a_lo + ko, b_hi + ko, idesc, 1);
-                    }
-                    tc::mma_commit(&empty[s]);                          // stage reusable when these MMAs retire
-                    if (c == nchunks - 1) tc::mma_commit(&tfull[acc]);  // accumulator complete
+        // ================= MMA issuer (leader CTA of the group) =================
+        if (cx.rank == 0) {
+            uint32_t it = 0, tcount = 0;
+            for (int tile = group; tile < num_tiles; tile += ngroups, ++tcount) {
+                const int acc = tcount & 1;
+                cx.mma_wait_tempty(acc, (tcount >> 1) & 1);
+                const uint32_t d_tmem = cx.tmem_base + (uint32_t)(acc * NT);
+                for (int c = 0; c < nchunks; ++c, ++it) {
+                    const int s = it % C::kStages;
+                    cx.mma_wait_full(s, (it / C::kStages) & 1);
+                    if (lane == 0) cx.issue_stage(s, d_tmem, c == 0, c == nchunks - 1, acc);
+                    __syncwarp();
                 }
-                __syncwarp();
             }
         }
     } else {
         // ================= epilogue =================
         const int q = warp & 3;                      // TMEM lane quarter this warp may access
         uint32_t tcount = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
+        for (int tile = group; tile < num_tiles; tile += ngroups, ++tcount) {
             const int b = tile / tiles_per_img, t = tile % tiles_per_img;
-            const int i0 = (t / tiles_j) * C::kM, j0 = (t % tiles_j) * NT;
+            const int i0 = (t / tiles_j) * kTileM + (int)cx.rank * C::kM, j0 = (t % tiles_j) * NT;
             const int acc = tcount & 1;
-            const uint32_t aph = (tcount >> 1) & 1;
-            tc::mbar_wait(&tfull[acc], aph);
+            tc::mbar_wait_sleep(&cx.tfull[acc], (tcount >> 1) & 1);
             tc::tc_fence_after();
             const int i = i0 + q * 32 + lane;
             float* dst = img + ((size_t)b * R + i) * R + j0;
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * NT);
+            const uint32_t taddr = cx.tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * NT);
             const bool vec = (R & 3) == 0;
 #pragma unroll 1
             for (int cb = 0; cb < NT; cb += 32) {
@@ -222,17 +315,10 @@ splat_fwd_tc_kernel(const float4* __restrict__ params, float* __restrict__ img, 
                     }
                 }
             }
-            tc::tc_fence_before();
-            tc::mbar_arrive(&tempty[acc]);
+            cx.epilogue_release(acc);
         }
     }
-    // ---- teardown ----
-    tc::tc_fence_before();
-    __syncthreads();
-    if (warp == C::kMmaWarp) {
-        tc::tc_fence_after();
-        tc::tmem_dealloc(tmem_base, C::kTmemCols);
-    }
+    cx.teardown();
 }
 
 inline bool splat_tc_fwd_supported(int B, int N, int R) { return B > 0 && N > 0 && R >= 8 && R <= kTcMaxR; }
@@ -241,111 +327,86 @@ inline bool splat_tc_fwd_preferred(int B, int N, int R) {
     return R >= 128 && N >= 64;
 }
 
-template <int NT>
-inline cudaError_t launch_splat_fwd_tc(const float* params, float* img, int B, int N, int R, float width, float height,
-                                       int num_sms, cudaStream_t st) {
-    using C = SplatFwdTc<NT>;
-    const int tiles_i = (R + C::kM - 1) / C::kM, tiles_j = (R + NT - 1) / NT;
-    const long long num_tiles = (long long)B * tiles_i * tiles_j;
-    if (num_tiles > 0x7fffffffLL) return cudaErrorInvalidValue;
-    cudaError_t e = cudaFuncSetAttribute(splat_fwd_tc_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+// launch `kernel` as a persistent grid of CTA groups (clusters of CG CTAs)
+template <int CG, class Kernel, class... Args>
+inline cudaError_t launch_tc_groups(Kernel kernel, long long num_tiles, int num_sms, int threads, int smem_bytes,
+                                    cudaStream_t st, Args... args) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) return e;
-    const int grid = (int)(num_tiles < num_sms ? num_tiles : num_sms);
-    splat_fwd_tc_kernel<NT><<<grid, C::kThreads, C::kSmemBytes, st>>>(reinterpret_cast<const float4*>(params), img, N, R,
-                                                                      make_axis(width, R), make_axis(height, R), tiles_i,
-                                                                      tiles_j, (int)num_tiles);
-    return cudaGetLastError();
+    long long groups = num_sms / CG;
+    if (num_tiles < groups) groups = num_tiles;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(groups * CG));
+    cfg.blockDim = dim3((unsigned)threads);
+    cfg.dynamicSmemBytes = (size_t)smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = CG > 1 ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, args...);
 }
 
+template <int NT, int CG>
+inline cudaError_t launch_splat_fwd_tc(const float* params, float* img, int B, int N, int R, float width, float height,
+                                       int num_sms, cudaStream_t st) {
+    using C = SplatFwdTc<NT, CG>;
+    const int tiles_i = (R + C::kM * CG - 1) / (C::kM * CG), tiles_j = (R + NT - 1) / NT;
+    const long long num_tiles = (long long)B * tiles_i * tiles_j;
+    if (num_tiles > 0x7fffffffLL) return cudaErrorInvalidValue;
+    return launch_tc_groups<CG>(splat_fwd_tc_kernel<NT, CG>, num_tiles, num_sms, C::kThreads, C::kSmemBytes, st,
+                                reinterpret_cast<const float4*>(params), img, N, R, make_axis(width, R), make_axis(height, R),
+                                tiles_i, tiles_j, (int)num_tiles);
+}
+
+// pair = 0: auto (CTA pairs for images taller than 128 rows), 1: single CTA, 2: CTA pairs
 inline cudaError_t splat_tc_fwd(const float* params, float* img, int B, int N, int R, float width, float height, int num_sms,
-                                cudaStream_t st) {
-    if (R > 128) return launch_splat_fwd_tc<256>(params, img, B, N, R, width, height, num_sms, st);
-    return launch_splat_fwd_tc<128>(params, img, B, N, R, width, height, num_sms, st);
+                                cudaStream_t st, int pair = 0) {
+    if (R > 128) {
+        if (pair != 1 && num_sms >= 2) return launch_splat_fwd_tc<256, 2>(params, img, B, N, R, width, height, num_sms, st);
+        return launch_splat_fwd_tc<256, 1>(params, img, B, N, R, width, height, num_sms, st);
+    }
+    return launch_splat_fwd_tc<128, 1>(params, img, B, N, R, width, height, num_sms, st);
 }
 
 // ================================================================================================
 // backward
 // ================================================================================================
-// Tile = (sun b, block of 128 heliostats).  Per tile two products run back to back through the
-// same pipeline, each split into ceil(R/NT) accumulators of 128 x NT:
+// Tile = (sun b, block of 128*CG heliostats, 128 per CTA).  Per tile two products run back to back
+// through the same pipeline, each split into ceil(R/NT) accumulators of 128 x NT per CTA:
 //   product 0 (T): A rows = Gy[n, j-chunk]       B rows = g[i, j-chunk]   (i = accumulator column)
 //   product 1 (U): A rows = amp Gx[n, i-chunk]   B rows = g[i-chunk, j]^T (j = accumulator column)
 // The epilogue thread that owns TMEM lane n keeps {S0,Sx,Sxx} from product 0 in registers, adds
 // {Sy,Syy} from product 1 and writes one float4 per heliostat.
-template <int NT>
-struct SplatBwdTc {
-    static constexpr int kNT = NT;                       // UMMA N (pixels per accumulator)
-    static constexpr int kM = 128;                       // UMMA M (heliostats per tile)
-    static constexpr int kKC = 32;                       // pixels per stage
-    static constexpr int kStages = (NT == 256) ? 2 : (NT == 128 ? 3 : 4);
-    static constexpr int kAWarps = kM / 32;              // Gaussian-operand producers
-    static constexpr int kGWarps = NT / 32;              // gradient-tile stagers
-    static constexpr int kMmaWarp = kAWarps + kGWarps;
-    static constexpr int kEpiWarp0 = kMmaWarp + 1;
-    static constexpr int kThreads = (kEpiWarp0 + 4) * 32;
-    static constexpr int kABytes = kM * 128;
-    static constexpr int kGBytes = NT * 128;
-    static constexpr int kStageBytes = 2 * kABytes + 2 * kGBytes;
-    static constexpr int kTmemCols = 2 * NT;
-    static constexpr int kTableBytes = 2 * kTcMaxR * 4;
-    static constexpr int kSmemBytes = kStages * kStageBytes + kTableBytes + 1024 + 256;
-    static_assert(kTmemCols <= 512 && (kTmemCols & (kTmemCols - 1)) == 0 && kTmemCols >= 32, "TMEM columns");
-    static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
-};
+template <int NT, int CG>
+using SplatBwdTc = SplatTcLayout<NT, CG, NT / CG>;
 
-template <int NT>
-__global__ void __launch_bounds__(SplatBwdTc<NT>::kThreads, 1)
+template <int NT, int CG>
+__global__ void __launch_bounds__(SplatBwdTc<NT, CG>::kThreads, 1)
 splat_bwd_tc_kernel(const float4* __restrict__ params, const float* __restrict__ g_img, float4* __restrict__ moments,
                     int N, int R, Axis ax, Axis ay, int nblocks, int num_tiles) {
-    using C = SplatBwdTc<NT>;
+    using C = SplatBwdTc<NT, CG>;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    float* sX = reinterpret_cast<float*>(smem + C::kStages * C::kStageBytes);
-    float* sY = sX + kTcMaxR;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sY + kTcMaxR);
-    uint64_t* full = bars;
-    uint64_t* empty = bars + C::kStages;
-    uint64_t* tfull = bars + 2 * C::kStages;
-    uint64_t* tempty = tfull + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    SplatTcCtx<C, CG> cx;
+    cx.setup(smem_raw, R, ax, ay);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-    for (int i = threadIdx.x; i < kTcMaxR; i += C::kThreads) {
-        sX[i] = i < R ? axis_at(ax, i) : 0.f;
-        sY[i] = i < R ? axis_at(ay, i) : 0.f;
-    }
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < C::kStages; ++s) {
-            tc::mbar_init(&full[s], C::kAWarps + C::kGWarps);
-            tc::mbar_init(&empty[s], 1);
-        }
-        for (int a = 0; a < 2; ++a) {
-            tc::mbar_init(&tfull[a], 1);
-            tc::mbar_init(&tempty[a], 128);
-        }
-        tc::mbar_fence_init();
-    }
-    if (warp == C::kMmaWarp) {
-        tc::tmem_alloc(tmem_slot, C::kTmemCols);
-        tc::tmem_relinquish();
-    }
-    tc::tc_fence_before();
-    __syncthreads();
-    tc::tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
     const int kchunks = (R + C::kKC - 1) / C::kKC;   // K stages per accumulator
     const int pblocks = (R + NT - 1) / NT;           // accumulators per product
     const bool vec = (R & 3) == 0;
+    const int group = blockIdx.x / CG, ngroups = gridDim.x / CG;
+    constexpr int kTileH = C::kM * CG;               // heliostats per tile
 
     if (warp < C::kAWarps) {
         // ================= Gaussian operand: thread = heliostat row =================
         const int r = threadIdx.x;
         uint32_t it = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int tile = group; tile < num_tiles; tile += ngroups) {
             const int b = tile / nblocks, nb = tile % nblocks;
-            const int n = nb * C::kM + r;
+            const int n = nb * kTileH + (int)cx.rank * C::kM + r;
             const bool live = n < N;
             const float4 p = live ? __ldg(params + (size_t)b * N + n) : make_float4(0.f, 0.f, 0.f, 0.f);
             const float nk2 = -p.z;
@@ -353,17 +414,15 @@ splat_bwd_tc_kernel(const float4* __restrict__ params, const float* __restrict__
             for (int prod = 0; prod < 2; ++prod) {
                 const float ctr = prod == 0 ? p.y : p.x;
                 const float scale = live ? (prod == 0 ? 1.f : p.w) : 0.f;
-                const float* tab = prod == 0 ? sY : sX;
+                const float* tab = prod == 0 ? cx.sY : cx.sX;
 #pragma unroll 1
                 for (int pbk = 0; pbk < pblocks; ++pbk) {
 #pragma unroll 1
                     for (int c = 0; c < kchunks; ++c, ++it) {
                         const int s = it % C::kStages;
-                        const uint32_t ph = (it / C::kStages) & 1;
                         const int k0 = c * C::kKC;
-                        if (lane == 0) tc::mbar_wait(&empty[s], ph ^ 1);
-                        __syncwarp();
-                        uint8_t* hi_base = smem + s * C::kStageBytes;
+                        cx.producer_acquire(s, (it / C::kStages) & 1);
+                        uint8_t* hi_base = cx.smem + s * C::kStageBytes;
                         uint8_t* lo_base = hi_base + C::kABytes;
 #pragma unroll
                         for (int q = 0; q < 8; ++q) {
@@ -381,19 +440,18 @@ splat_bwd_tc_kernel(const float4* __restrict__ params, const float* __restrict__
                             *reinterpret_cast<float4*>(hi_base + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
                             *reinterpret_cast<float4*>(lo_base + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
                         }
-                        tc::fence_proxy_async_smem();
-                        __syncwarp();
-                        if (lane == 0) tc::mbar_arrive(&full[s]);
+                        cx.producer_commit(s);
                     }
                 }
             }
         }
     } else if (warp < C::kMmaWarp) {
         // ================= gradient tile stagers =================
-        const int t = threadIdx.x - C::kAWarps * 32;     // 0..NT-1
+        const int t = threadIdx.x - C::kAWarps * 32;     // 0..kBRows-1: operand row inside this CTA's share
         const int gw = t >> 5;
+        const int row_base = (int)cx.rank * C::kBRows;   // first accumulator column this CTA stages
         uint32_t it = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int tile = group; tile < num_tiles; tile += ngroups) {
             const int b = tile / nblocks;
             const float* gb = g_img + (size_t)b * R * R;
 #pragma unroll 1
@@ -403,7 +461,6 @@ splat_bwd_tc_kernel(const float4* __restrict__ params, const float* __restrict__
 #pragma unroll 1
                     for (int c = 0; c < kchunks; ++c, ++it) {
                         const int s = it % C::kStages;
-                        const uint32_t ph = (it / C::kStages) & 1;
                         const int k0 = c * C::kKC;
                         float4 vals[8];
                         uint32_t offs[8];
@@ -413,7 +470,7 @@ splat_bwd_tc_kernel(const float4* __restrict__ params, const float* __restrict__
 #pragma unroll
                             for (int q = 0; q < 8; ++q) {
                                 const int row = gw * 32 + q * 4 + (lane >> 3), ch = lane & 7;
-                                const int i = pbk * NT + row, j = k0 + ch * 4;
+                                const int i = pbk * NT + row_base + row, j = k0 + ch * 4;
                                 float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                                 if (i < R) {
                                     const float* src = gb + (size_t)i * R + j;
@@ -432,7 +489,7 @@ splat_bwd_tc_kernel(const float4* __restrict__ params, const float* __restrict__
                         } else {
                             // operand row = image column j (accumulator column), K = image row i:
                             // lanes read consecutive columns of one image row (coalesced), transposing in registers
-                            const int j = pbk * NT + t;
+                            const int j = pbk * NT + row_base + t;
 #pragma unroll
                             for (int q = 0; q < 8; ++q) {
                                 float x[4];
@@ -445,10 +502,9 @@ splat_bwd_tc_kernel(const float4* __restrict__ params, const float* __restrict__
                                 offs[q] = tc::sw128_offset((uint32_t)t, (uint32_t)q);
                             }
                         }
-                        if (lane == 0) tc::mbar_wait(&empty[s], ph ^ 1);
-                        __syncwarp();
-                        uint8_t* hi_base = smem + s * C::kStageBytes + 2 * C::kABytes;
-                        uint8_t* lo_base = hi_base + C::kGBytes;
+                        cx.producer_acquire(s, (it / C::kStages) & 1);
+                        uint8_t* hi_base = cx.smem + s * C::kStageBytes + 2 * C::kABytes;
+                        uint8_t* lo_base = hi_base + C::kBBytes;
 #pragma unroll
                         for (int q = 0; q < 8; ++q) {
                             float4 h, l;
@@ -459,47 +515,27 @@ splat_bwd_tc_kernel(const float4* __restrict__ params, const float* __restrict__
                             *reinterpret_cast<float4*>(hi_base + offs[q]) = h;
                             *reinterpret_cast<float4*>(lo_base + offs[q]) = l;
                         }
-                        tc::fence_proxy_async_smem();
-                        __syncwarp();
-                        if (lane == 0) tc::mbar_arrive(&full[s]);
+                        cx.producer_commit(s);
                     }
                 }
             }
         }
     } else if (warp == C::kMmaWarp) {
-        // ================= MMA issuer =================
-        constexpr uint32_t idesc = tc::make_idesc_tf32(C::kM, NT);
-        uint32_t it = 0, sub = 0;
-        const int subs_per_tile = 2 * pblocks;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            for (int sb = 0; sb < subs_per_tile; ++sb, ++sub) {
-                const int acc = sub & 1;
-                const uint32_t aph = (sub >> 1) & 1;
-                tc::mbar_wait(&tempty[acc], aph ^ 1);
-                tc::tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * NT);
-                for (int c = 0; c < kchunks; ++c, ++it) {
-                    const int s = it % C::kStages;
-                    const uint32_t ph = (it / C::kStages) & 1;
-                    tc::mbar_wait(&full[s], ph);
-                    tc::tc_fence_after();
-                    if (lane == 0) {
-                        const uint32_t sa = tc::smem_u32(smem + s * C::kStageBytes);
-                        const uint64_t a_hi = tc::make_desc_k_sw128(sa);
-                        const uint64_t a_lo = tc::make_desc_k_sw128(sa + C::kABytes);
-                        const uint64_t b_hi = tc::make_desc_k_sw128(sa + 2 * C::kABytes);
-                        const uint64_t b_lo = tc::make_desc_k_sw128(sa + 2 * C::kABytes + C::kGBytes);
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const uint64_t ko = (uint64_t)(k * 32 >> 4);
-                            tc::mma_tf32_ss(d_tmem, a_hi + ko, b_hi + ko, idesc, (c | k) != 0);
-                            tc::mma_tf32_ss(d_tmem, a_hi + ko, b_lo + ko, idesc, 1);
-                            tc::mma_tf32_ss(d_tmem, a_lo + ko, b_hi + ko, idesc, 1);
-                        }
-                        tc::mma_commit(&empty[s]);
-                        if (c == kchunks - 1) tc::mma_commit(&tfull[acc]);
+        // ================= MMA issuer (leader CTA of the group) =================
+        if (cx.rank == 0) {
+            uint32_t it = 0, sub = 0;
+            const int subs_per_tile = 2 * pblocks;
+            for (int tile = group; tile < num_tiles; tile += ngroups) {
+                for (int sb = 0; sb < subs_per_tile; ++sb, ++sub) {
+                    const int acc = sub & 1;
+                    cx.mma_wait_tempty(acc, (sub >> 1) & 1);
+                    const uint32_t d_tmem = cx.tmem_base + (uint32_t)(acc * NT);
+                    for (int c = 0; c < kchunks; ++c, ++it) {
+                        const int s = it % C::kStages;
+                        cx.mma_wait_full(s, (it / C::kStages) & 1);
+                        if (lane == 0) cx.issue_stage(s, d_tmem, c == 0, c == kchunks - 1, acc);
+                        __syncwarp();
                     }
-                    __syncwarp();
                 }
             }
         }
@@ -507,9 +543,9 @@ splat_bwd_tc_kernel(const float4* __restrict__ params, const float* __restrict__
         // ================= epilogue: accumulator -> moments =================
         const int q = warp & 3;
         uint32_t sub = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int tile = group; tile < num_tiles; tile += ngroups) {
             const int b = tile / nblocks, nb = tile % nblocks;
-            const int n = nb * C::kM + q * 32 + lane;
+            const int n = nb * kTileH + (int)cx.rank * C::kM + q * 32 + lane;
             const bool live = n < N;
             const float4 p = live ? __ldg(params + (size_t)b * N + n) : make_float4(0.f, 0.f, 0.f, 0.f);
             const float nk2 = -p.z;
@@ -517,15 +553,14 @@ splat_bwd_tc_kernel(const float4* __restrict__ params, const float* __restrict__
 #pragma unroll 1
             for (int prod = 0; prod < 2; ++prod) {
                 const float ctr = prod == 0 ? p.x : p.y;
-                const float* tab = prod == 0 ? sX : sY;
+                const float* tab = prod == 0 ? cx.sX : cx.sY;
                 float s0 = 0.f, s1 = 0.f, s2 = 0.f;
 #pragma unroll 1
                 for (int pbk = 0; pbk < pblocks; ++pbk, ++sub) {
                     const int acc = sub & 1;
-                    const uint32_t aph = (sub >> 1) & 1;
-                    tc::mbar_wait(&tfull[acc], aph);
+                    tc::mbar_wait_sleep(&cx.tfull[acc], (sub >> 1) & 1);
                     tc::tc_fence_after();
-                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * NT);
+                    const uint32_t taddr = cx.tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * NT);
                     const int col0 = pbk * NT;
 #pragma unroll 1
                     for (int cb = 0; cb < NT; cb += 32) {
@@ -547,8 +582,7 @@ splat_bwd_tc_kernel(const float4* __restrict__ params, const float* __restrict__
                             }
                         }
                     }
-                    tc::tc_fence_before();
-                    tc::mbar_arrive(&tempty[acc]);
+                    cx.epilogue_release(acc);
                 }
                 if (prod == 0) {
                     S0 = s0 * p.w, Sx = s1 * p.w, S2 = s2 * p.w;
@@ -559,38 +593,34 @@ splat_bwd_tc_kernel(const float4* __restrict__ params, const float* __restrict__
             if (live) moments[(size_t)b * N + n] = make_float4(S0, Sx, Sy, S2);
         }
     }
-    tc::tc_fence_before();
-    __syncthreads();
-    if (warp == C::kMmaWarp) {
-        tc::tc_fence_after();
-        tc::tmem_dealloc(tmem_base, C::kTmemCols);
-    }
+    cx.teardown();
 }
 
 inline bool splat_tc_bwd_supported(int B, int N, int R) { return B > 0 && N > 0 && R >= 8 && R <= kTcMaxR; }
 inline bool splat_tc_bwd_preferred(int B, int N, int R) { return R >= 128 && N >= 64; }
 
-template <int NT>
+template <int NT, int CG>
 inline cudaError_t launch_splat_bwd_tc(const float* params, const float* g_img, float* moments, int B, int N, int R,
                                        float width, float height, int num_sms, cudaStream_t st) {
-    using C = SplatBwdTc<NT>;
-    const int nblocks = (N + C::kM - 1) / C::kM;
+    using C = SplatBwdTc<NT, CG>;
+    const int nblocks = (N + C::kM * CG - 1) / (C::kM * CG);
     const long long num_tiles = (long long)B * nblocks;
     if (num_tiles > 0x7fffffffLL) return cudaErrorInvalidValue;
-    cudaError_t e = cudaFuncSetAttribute(splat_bwd_tc_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
-    if (e != cudaSuccess) return e;
-    const int grid = (int)(num_tiles < num_sms ? num_tiles : num_sms);
-    splat_bwd_tc_kernel<NT><<<grid, C::kThreads, C::kSmemBytes, st>>>(
-        reinterpret_cast<const float4*>(params), g_img, reinterpret_cast<float4*>(moments), N, R, make_axis(width, R),
-        make_axis(height, R), nblocks, (int)num_tiles);
-    return cudaGetLastError();
+    return launch_tc_groups<CG>(splat_bwd_tc_kernel<NT, CG>, num_tiles, num_sms, C::kThreads, C::kSmemBytes, st,
+                                reinterpret_cast<const float4*>(params), g_img, reinterpret_cast<float4*>(moments), N, R,
+                                make_axis(width, R), make_axis(height, R), nblocks, (int)num_tiles);
 }
 
 inline cudaError_t splat_tc_bwd(const float* params, const float* g_img, float* moments, int B, int N, int R, float width,
-                                float height, int num_sms, cudaStream_t st) {
-    if (R > 128) return launch_splat_bwd_tc<256>(params, g_img, moments, B, N, R, width, height, num_sms, st);
-    if (R > 64) return launch_splat_bwd_tc<128>(params, g_img, moments, B, N, R, width, height, num_sms, st);
-    return launch_splat_bwd_tc<64>(params, g_img, moments, B, N, R, width, height, num_sms, st);
+                                float height, int num_sms, cudaStream_t st, int pair = 0) {
+    if (R > 128) {
+        // CTA pairs need a second block of 128 heliostats to be worth it
+        if (pair != 1 && num_sms >= 2 && (pair == 2 || N > 128))
+            return launch_splat_bwd_tc<256, 2>(params, g_img, moments, B, N, R, width, height, num_sms, st);
+        return launch_splat_bwd_tc<256, 1>(params, g_img, moments, B, N, R, width, height, num_sms, st);
+    }
+    if (R > 64) return launch_splat_bwd_tc<128, 1>(params, g_img, moments, B, N, R, width, height, num_sms, st);
+    return launch_splat_bwd_tc<64, 1>(params, g_img, moments, B, N, R, width, height, num_sms, st);
 }
 
 }  // namespace helio

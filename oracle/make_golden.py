@@ -126,6 +126,7 @@ def env_case(ref_env, name, seed, N, R, B, sigma_scale, err_mrad, helio_fn, **kw
         sun_pos=npy(sun_pos), distance_maps=npy(dmaps0), ref_min=npy(env.ref_min), ref_max=npy(env.ref_max),
         errs=npy(errs), err_single=npy(err1), reset_img=npy(obs0["img"]), reset_aux=npy(obs0["aux"]), reset_action=npy(reset_action),
         ideal=npy(env.ideal_normals), action=npy(action), target=npy(target),
+        ref_init_action=npy(env.ref_field.initial_action),   # ideal + N(0, 0.01) drawn inside set_sun_pos (test_environment.py:363)
         step_img=npy(obs["img"]), step_aux=npy(obs["aux"]),
         **{f"metric_{k}": npy(v) for k, v in metrics.items()},
         **{f"monitor_{k}": npy(v) for k, v in monitor.items()},

@@ -77,6 +77,8 @@ def _env_from_golden(g, **kw):
                    targ_norm=_t(g["targ_norm"]), sigma_scale=float(g["sigma_scale"]), error_scale_mrad=float(g["err_mrad"]),
                    initial_action_noise=0.0, resolution=int(g["R"]), batch_size=int(g["B"]), device="cuda:0",
                    use_error_mask=bool(g["use_error_mask"]), exponential_risk=bool(g["exponential_risk"]), **kw)
+    # set_sun_pos draws ideal + N(0, 0.01) inside ref_field.init_actions (test_environment.py:363); pin the draw
+    env.ref_field.init_actions = lambda sun: setattr(env.ref_field, "initial_action", _t(g["ref_init_action"]))
     env.set_sun_pos(_t(g["sun_pos"]))
     env.noisy_field.batch_error_angles_mrad = _t(g["errs"])
     env.noisy_field.error_angles_mrad = _t(g["err_single"])
@@ -89,12 +91,13 @@ def test_env_step_matches_reference(name, cache):
     g = load_golden("env_" + name)
     env = _env_from_golden(g, cache_target=cache)
     B, R = int(g["B"]), int(g["R"])
-    # set_sun_pos products (test_environment.py:359-370).  The distance maps threshold a render of
-    # ideal + N(0, 0.01) noise (ref_field.init_actions), so they depend on the RNG stream: compare loosely,
-    # then pin the reference's maps for the loss checks.
+    # set_sun_pos products (test_environment.py:359-370): target render -> threshold at 0.5*max -> scipy EDT.
+    # A pixel within 1e-4 of the threshold may flip between two fp32 renders and moves distances by <= 1 pixel.
     assert env.distance_maps.shape == g["distance_maps"].shape
-    assert float((env.distance_maps.cpu() - torch.as_tensor(g["distance_maps"])).abs().max()) <= 2.0
-    np.testing.assert_allclose(float(env.ref_max), float(g["ref_max"]), rtol=5e-2)
+    dm_err = (env.distance_maps.cpu() - torch.as_tensor(g["distance_maps"])).abs()
+    assert float(dm_err.max()) <= 1.0 and float((dm_err > 1e-4).float().mean()) < 0.02
+    np.testing.assert_allclose(float(env.ref_max), float(g["ref_max"]), rtol=1e-4)
+    np.testing.assert_allclose(float(env.ref_min), float(g["ref_min"]), rtol=1e-4, atol=1e-6)
     env.distance_maps = _t(g["distance_maps"])
     for rep in range(2 if cache else 1):      # second pass exercises the cached target
         action = _t(g["action"]).requires_grad_(True)
@@ -102,12 +105,18 @@ def test_env_step_matches_reference(name, cache):
         np.testing.assert_allclose(obs["img"].detach().cpu().numpy(), g["step_img"], **IMG_TOL)
         np.testing.assert_allclose(obs["aux"].detach().cpu().numpy(), g["step_aux"], rtol=1e-6)
         for k in ("mse", "dist", "bound", "alignment_loss"):
-            np.testing.assert_allclose(float(metrics[k]), float(g["metric_" + k]), rtol=2e-4, err_msg=k)
+            np.testing.assert_allclose(float(metrics[k].detach()), float(g["metric_" + k]), rtol=2e-4, err_msg=k)
         for k in ("normals", "reflected_rays", "ideal_normals", "all_bounds", "mae_image", "alignment_errors"):
             ref = g["monitor_" + k]
             got = monitor[k].detach().cpu().numpy()
             assert got.shape == ref.shape, k
-            np.testing.assert_allclose(got, ref, rtol=2e-4, atol=1e-3 if k == "alignment_errors" else 1e-5, err_msg=k)
+            if k == "alignment_errors":
+                # angle = 1000*acos(dot): a 2-ulp difference of the fp32 dot product (~1.2e-7 near 1) moves the
+                # angle by 1000*1.2e-7/sin(angle) mrad, which dominates for well-aligned mirrors
+                tol = 2e-4 * np.abs(ref) + 1000.0 * 2.4e-7 / np.maximum(np.sin(ref * 1e-3), 3.4e-4)
+                assert np.all(np.abs(got - ref) <= tol), (k, np.abs(got - ref).max())
+            else:
+                np.testing.assert_allclose(got, ref, rtol=2e-4, atol=1e-5, err_msg=k)
         for k in ("mse", "dist", "bound", "alignment_loss"):
             gr, = torch.autograd.grad(metrics[k], action, retain_graph=True, allow_unused=True)
             assert rel_err(gr.cpu().numpy(), g["grad_" + k]) < GRAD_TOL, k
