@@ -185,13 +185,11 @@ struct SplatTcCtx {
         }
     }
     __device__ __forceinline__ void mma_wait_full(int s, uint32_t ph) const {
-        if constexpr (CG == 2) tc::mbar_wait_cluster(&full[s], ph);
-        else tc::mbar_wait(&full[s], ph);
+        tc::mbar_wait(&full[s], ph);
         tc::tc_fence_after();
     }
     __device__ __forceinline__ void mma_wait_tempty(int acc, uint32_t aph) const {
-        if constexpr (CG == 2) tc::mbar_wait_cluster(&tempty[acc], aph ^ 1);
-        else tc::mbar_wait(&tempty[acc], aph ^ 1);
+        tc::mbar_wait(&tempty[acc], aph ^ 1);
         tc::tc_fence_after();
     }
 };
@@ -202,10 +200,10 @@ struct SplatTcCtx {
 template <int NT, int CG>
 using SplatFwdTc = SplatTcLayout<NT, CG, NT / CG>;
 
-// Producer mapping: a warp owns 32 operand rows (image rows for A, image columns for B) and its
-// lanes own the 32 heliostats of the stage, so the footprint parameters sit in registers (one
-// coalesced 512-byte load per warp and stage, prefetched one stage ahead) and every store is one
-// conflict-free 128-byte row of the swizzled tile.
+// Producer mapping: a warp owns 32 operand rows (image rows for A, image columns for B); a lane owns
+// 4 consecutive heliostats of the stage (one 16-byte chunk of the K-major row) and walks 8 of the
+// rows, so the footprint parameters sit in registers (loaded once per stage, prefetched one stage
+// ahead) and every warp store writes four full 128-byte rows of the swizzled tile, conflict-free.
 template <int NT, int CG>
 __global__ void __launch_bounds__(SplatFwdTc<NT, CG>::kThreads, 1)
 splat_fwd_tc_kernel(const float4* __restrict__ params, float* __restrict__ img, int N, int R, Axis ax, Axis ay,
@@ -223,47 +221,58 @@ splat_fwd_tc_kernel(const float4* __restrict__ params, float* __restrict__ img, 
 
     if (warp < C::kMmaWarp) {
         // ================= producers =================
+        // lane = (row subgroup rs = lane >> 3, K chunk ch = lane & 7): per step a warp covers 4 operand rows x
+        // 32 heliostats, each lane evaluating its 4 heliostats for one row and storing them as one 16-byte chunk.
         const bool isA = warp < C::kAWarps;
         const int wrow = (isA ? warp : warp - C::kAWarps) * 32;          // first operand row of this warp (CTA-local)
+        const int rs = lane >> 3, ch = lane & 7;
         const uint32_t region = (isA ? 0u : 2u * C::kABytes) + (uint32_t)(wrow >> 3) * 1024u;
         const uint32_t lo_delta = isA ? C::kABytes : C::kBBytes;
-        // byte offset of this lane's element inside a 128-byte row whose (row & 7) == c
-        uint32_t xoff[8];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) xoff[c] = ((((uint32_t)lane >> 2) ^ (uint32_t)c) << 4) + ((uint32_t)lane & 3u) * 4u;
+        // rows visited by this lane: wrow + 4*step + rs, step = 0..7; (row & 7) = 4*(step & 1) + rs
+        const uint32_t off_even = (uint32_t)rs * 128u + (((uint32_t)ch ^ (uint32_t)rs) << 4);
+        const uint32_t off_odd = (uint32_t)(rs + 4) * 128u + (((uint32_t)ch ^ (uint32_t)(rs + 4)) << 4);
         uint32_t it = 0;                             // global stage counter
         for (int tile = group; tile < num_tiles; tile += ngroups) {
             const int b = tile / tiles_per_img, t = tile % tiles_per_img;
             const int g0 = (isA ? (t / tiles_j) * kTileM + (int)cx.rank * C::kM : (t % tiles_j) * NT + (int)cx.rank * C::kBRows) + wrow;
-            const float* tab = (isA ? cx.sX : cx.sY) + g0;
-            float xr[32];
+            const float* tab = (isA ? cx.sX : cx.sY) + g0 + rs;
+            float xr[8];
 #pragma unroll
-            for (int e = 0; e < 32; e += 4) {
-                const float4 v = *reinterpret_cast<const float4*>(tab + e);
-                xr[e] = v.x, xr[e + 1] = v.y, xr[e + 2] = v.z, xr[e + 3] = v.w;
-            }
+            for (int st = 0; st < 8; ++st) xr[st] = tab[4 * st];
             const float4* pb = params + (size_t)b * N;
-            float4 pn = lane < N ? __ldg(pb + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+            // this lane's 4 heliostats of the stage, prefetched one stage ahead as raw float4 (index clamped so the
+            // load never needs a select: nothing touches the loaded registers until the next stage decodes them)
+            float4 pr[4];
+            auto prefetch = [&](int c) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) pr[e] = __ldg(pb + min(c * C::kKC + 4 * ch + e, N - 1));
+            };
+            prefetch(0);
             for (int c = 0; c < nchunks; ++c, ++it) {
-                const float4 p = pn;
-                const bool have = c * C::kKC + lane < N;
-                const int nn = (c + 1) * C::kKC + lane;
-                pn = nn < N ? __ldg(pb + nn) : make_float4(0.f, 0.f, 0.f, 0.f);
-                const float ctr = isA ? p.x : p.y;
-                const float nk2 = -p.z;
-                const float scale = have ? (isA ? p.w : 1.f) : 0.f;     // K padding: exact zeros
+                float ctr[4], nk2[4], scl[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const bool have = c * C::kKC + 4 * ch + e < N;
+                    ctr[e] = isA ? pr[e].x : pr[e].y;
+                    nk2[e] = -pr[e].z;
+                    scl[e] = have ? (isA ? pr[e].w : 1.f) : 0.f;           // K padding: exact zeros
+                }
+                prefetch(c + 1 < nchunks ? c + 1 : c);
                 const int s = it % C::kStages;
                 cx.producer_acquire(s, (it / C::kStages) & 1);
                 uint8_t* base = cx.smem + s * C::kStageBytes + region;
 #pragma unroll
-                for (int e = 0; e < 32; ++e) {
-                    const float d = xr[e] - ctr;
-                    const float v = ex2((d * nk2) * d) * scale;
-                    float hi, lo;
-                    tc::split_tf32(v, hi, lo);
-                    uint8_t* dst = base + (e >> 3) * 1024 + (e & 7) * 128 + xoff[e & 7];
-                    *reinterpret_cast<float*>(dst) = hi;
-                    *reinterpret_cast<float*>(dst + lo_delta) = lo;
+                for (int st = 0; st < 8; ++st) {
+                    float hi[4], lo[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float d = xr[st] - ctr[e];
+                        const float v = ex2((d * nk2[e]) * d) * scl[e];
+                        tc::split_tf32(v, hi[e], lo[e]);
+                    }
+                    uint8_t* dst = base + (st >> 1) * 1024 + ((st & 1) ? off_odd : off_even);
+                    *reinterpret_cast<float4*>(dst) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                    *reinterpret_cast<float4*>(dst + lo_delta) = make_float4(lo[0], lo[1], lo[2], lo[3]);
                 }
                 cx.producer_commit(s);
             }

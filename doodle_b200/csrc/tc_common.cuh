@@ -94,27 +94,16 @@ __device__ __forceinline__ void cluster_sync() {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-// arrive on the mbarrier at the same shared-memory offset in CTA `rank` of the cluster
+// arrive on the mbarrier at the same shared-memory offset in CTA `rank` of the cluster.  Default semantics
+// (release at CTA scope): the data this guards is shared memory consumed by the async proxy, made visible by
+// fence.proxy.async before the arrive; a cluster-scope release would add MEMBAR.GPU + an L1 invalidate per call.
 __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
     asm volatile(
         "{\n\t.reg .b32 ra;\n\t"
         "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
         ::"r"(smem_u32(bar)), "r"(rank)
         : "memory");
-}
-// wait that also acquires arrivals made by the peer CTA
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.b32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(smem_u32(bar)), "r"(parity)
-            : "memory");
-    } while (!ok);
 }
 // long waits (epilogue waiting for a whole tile): back off so the spin does not eat issue slots
 __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
