@@ -71,7 +71,9 @@ struct SplatTcLayout {
 template <class C, int CG>
 struct SplatTcCtx {
     uint8_t* smem;        // operand stages (1024-byte aligned)
+    uint32_t smem_u;      // same, as a 32-bit shared-state-space address
     float *sX, *sY;       // pixel-centre tables
+    uint32_t sX_u, sY_u;
     uint64_t *full, *empty, *tfull, *tempty;
     uint32_t tmem_base;
     uint32_t rank;        // CTA rank inside the pair (0 when CG == 1)
@@ -80,6 +82,7 @@ struct SplatTcCtx {
         smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
         sX = reinterpret_cast<float*>(smem + C::kStages * C::kStageBytes);
         sY = sX + kTcMaxR;
+        smem_u = tc::smem_u32(smem), sX_u = tc::smem_u32(sX), sY_u = tc::smem_u32(sY);
         uint64_t* bars = reinterpret_cast<uint64_t*>(sY + kTcMaxR);
         full = bars;                       // [kStages]  producers -> MMA   (leader's copy is the live one)
         empty = bars + C::kStages;         // [kStages]  MMA -> producers
@@ -158,7 +161,7 @@ struct SplatTcCtx {
     // MMA thread: one stage = 4 K-steps x {hi*hi, hi*lo, lo*hi}; `first` clears the accumulator
     __device__ __forceinline__ void issue_stage(int s, uint32_t d_tmem, bool first, bool last, int acc) const {
         constexpr uint32_t idesc = tc::make_idesc_tf32(C::kM * CG, C::kNT);
-        const uint32_t sa = tc::smem_u32(smem + s * C::kStageBytes);
+        const uint32_t sa = smem_u + (uint32_t)(s * C::kStageBytes);
         const uint64_t a_hi = tc::make_desc_k_sw128(sa);
         const uint64_t a_lo = tc::make_desc_k_sw128(sa + C::kABytes);
         const uint64_t b_hi = tc::make_desc_k_sw128(sa + 2 * C::kABytes);
@@ -235,10 +238,10 @@ splat_fwd_tc_kernel(const float4* __restrict__ params, float* __restrict__ img, 
         for (int tile = group; tile < num_tiles; tile += ngroups) {
             const int b = tile / tiles_per_img, t = tile % tiles_per_img;
             const int g0 = (isA ? (t / tiles_j) * kTileM + (int)cx.rank * C::kM : (t % tiles_j) * NT + (int)cx.rank * C::kBRows) + wrow;
-            const float* tab = (isA ? cx.sX : cx.sY) + g0 + rs;
+            const uint32_t tab = (isA ? cx.sX_u : cx.sY_u) + (uint32_t)(g0 + rs) * 4u;
             float xr[8];
 #pragma unroll
-            for (int st = 0; st < 8; ++st) xr[st] = tab[4 * st];
+            for (int st = 0; st < 8; ++st) xr[st] = tc::lds_f32(tab + 16u * st);
             const float4* pb = params + (size_t)b * N;
             // this lane's 4 heliostats of the stage, prefetched one stage ahead as raw float4 (index clamped so the
             // load never needs a select: nothing touches the loaded registers until the next stage decodes them)
@@ -260,7 +263,7 @@ splat_fwd_tc_kernel(const float4* __restrict__ params, float* __restrict__ img, 
                 prefetch(c + 1 < nchunks ? c + 1 : c);
                 const int s = it % C::kStages;
                 cx.producer_acquire(s, (it / C::kStages) & 1);
-                uint8_t* base = cx.smem + s * C::kStageBytes + region;
+                const uint32_t base = cx.smem_u + (uint32_t)(s * C::kStageBytes) + region;
 #pragma unroll
                 for (int st = 0; st < 8; ++st) {
                     float hi[4], lo[4];
@@ -270,9 +273,9 @@ splat_fwd_tc_kernel(const float4* __restrict__ params, float* __restrict__ img, 
                         const float v = ex2((d * nk2[e]) * d) * scl[e];
                         tc::split_tf32(v, hi[e], lo[e]);
                     }
-                    uint8_t* dst = base + (st >> 1) * 1024 + ((st & 1) ? off_odd : off_even);
-                    *reinterpret_cast<float4*>(dst) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-                    *reinterpret_cast<float4*>(dst + lo_delta) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                    const uint32_t dst = base + (uint32_t)(st >> 1) * 1024u + ((st & 1) ? off_odd : off_even);
+                    tc::sts_v4(dst, hi[0], hi[1], hi[2], hi[3]);
+                    tc::sts_v4(dst + lo_delta, lo[0], lo[1], lo[2], lo[3]);
                 }
                 cx.producer_commit(s);
             }
@@ -423,31 +426,32 @@ splat_bwd_tc_kernel(const float4* __restrict__ params, const float* __restrict__
             for (int prod = 0; prod < 2; ++prod) {
                 const float ctr = prod == 0 ? p.y : p.x;
                 const float scale = live ? (prod == 0 ? 1.f : p.w) : 0.f;
-                const float* tab = prod == 0 ? cx.sY : cx.sX;
+                const uint32_t tab = prod == 0 ? cx.sY_u : cx.sX_u;
 #pragma unroll 1
                 for (int pbk = 0; pbk < pblocks; ++pbk) {
 #pragma unroll 1
                     for (int c = 0; c < kchunks; ++c, ++it) {
                         const int s = it % C::kStages;
                         const int k0 = c * C::kKC;
+                        const bool tail = k0 + C::kKC > R;                      // warp-uniform: only the last chunk of a ragged R
                         cx.producer_acquire(s, (it / C::kStages) & 1);
-                        uint8_t* hi_base = cx.smem + s * C::kStageBytes;
-                        uint8_t* lo_base = hi_base + C::kABytes;
+                        const uint32_t hi_base = cx.smem_u + (uint32_t)(s * C::kStageBytes);
+                        const uint32_t lo_base = hi_base + C::kABytes;
 #pragma unroll
                         for (int q = 0; q < 8; ++q) {
-                            const float4 xs = *reinterpret_cast<const float4*>(tab + k0 + 4 * q);
+                            const float4 xs = tc::lds_v4(tab + (uint32_t)(k0 + 4 * q) * 4u);
                             const float x[4] = {xs.x, xs.y, xs.z, xs.w};
                             float hi[4], lo[4];
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
                                 const float d = x[e] - ctr;
                                 float v = ex2((d * nk2) * d) * scale;
-                                if (k0 + 4 * q + e >= R) v = 0.f;               // K padding: exact zeros
+                                if (tail && k0 + 4 * q + e >= R) v = 0.f;       // K padding: exact zeros
                                 tc::split_tf32(v, hi[e], lo[e]);
                             }
                             const uint32_t off = tc::sw128_offset((uint32_t)r, (uint32_t)q);
-                            *reinterpret_cast<float4*>(hi_base + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-                            *reinterpret_cast<float4*>(lo_base + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                            tc::sts_v4(hi_base + off, hi[0], hi[1], hi[2], hi[3]);
+                            tc::sts_v4(lo_base + off, lo[0], lo[1], lo[2], lo[3]);
                         }
                         cx.producer_commit(s);
                     }
@@ -512,8 +516,8 @@ splat_bwd_tc_kernel(const float4* __restrict__ params, const float* __restrict__
                             }
                         }
                         cx.producer_acquire(s, (it / C::kStages) & 1);
-                        uint8_t* hi_base = cx.smem + s * C::kStageBytes + 2 * C::kABytes;
-                        uint8_t* lo_base = hi_base + C::kBBytes;
+                        const uint32_t hi_base = cx.smem_u + (uint32_t)(s * C::kStageBytes + 2 * C::kABytes);
+                        const uint32_t lo_base = hi_base + C::kBBytes;
 #pragma unroll
                         for (int q = 0; q < 8; ++q) {
                             float4 h, l;
@@ -521,8 +525,8 @@ splat_bwd_tc_kernel(const float4* __restrict__ params, const float* __restrict__
                             tc::split_tf32(vals[q].y, h.y, l.y);
                             tc::split_tf32(vals[q].z, h.z, l.z);
                             tc::split_tf32(vals[q].w, h.w, l.w);
-                            *reinterpret_cast<float4*>(hi_base + offs[q]) = h;
-                            *reinterpret_cast<float4*>(lo_base + offs[q]) = l;
+                            tc::sts_v4(hi_base + offs[q], h.x, h.y, h.z, h.w);
+                            tc::sts_v4(lo_base + offs[q], l.x, l.y, l.z, l.w);
                         }
                         cx.producer_commit(s);
                     }
@@ -562,7 +566,7 @@ splat_bwd_tc_kernel(const float4* __restrict__ params, const float* __restrict__
 #pragma unroll 1
             for (int prod = 0; prod < 2; ++prod) {
                 const float ctr = prod == 0 ? p.x : p.y;
-                const float* tab = prod == 0 ? cx.sX : cx.sY;
+                const uint32_t tab = prod == 0 ? cx.sX_u : cx.sY_u;
                 float s0 = 0.f, s1 = 0.f, s2 = 0.f;
 #pragma unroll 1
                 for (int pbk = 0; pbk < pblocks; ++pbk, ++sub) {
@@ -578,7 +582,7 @@ splat_bwd_tc_kernel(const float4* __restrict__ params, const float* __restrict__
                         tc::tmem_ld_32x32(taddr + cb, v);
 #pragma unroll
                         for (int e4 = 0; e4 < 32; e4 += 4) {
-                            const float4 xs = *reinterpret_cast<const float4*>(tab + col0 + cb + e4);
+                            const float4 xs = tc::lds_v4(tab + (uint32_t)(col0 + cb + e4) * 4u);
                             const float x[4] = {xs.x, xs.y, xs.z, xs.w};
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {

@@ -36,6 +36,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // generic-proxy smem writes -> visible to the async proxy (tcgen05.mma operand reads)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// ---- explicit shared-state-space accesses (32-bit shared addresses) --------------------------
+// The operand tiles are addressed through pointers the compiler cannot prove to be shared memory; generic
+// LD/ST would go through the slower generic path (and the long scoreboard), so the hot loops use these.
+__device__ __forceinline__ void sts_v4(uint32_t addr, float a, float b, float c, float d) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ float4 lds_v4(uint32_t addr) {  // read-only tables: may be hoisted / CSE'd
+    float4 v;
+    asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+    float v;
+    asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+
 // ---- tcgen05 -------------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {  // one full warp
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
