@@ -41,7 +41,7 @@ FLOP_PER_EVAL = {"splat_fwd": 2.0, "splat_bwd": 4.0}
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--N", type=int, default=WORKLOAD["N"])
@@ -152,20 +152,61 @@ def main_reference(args):
 # GPU arm
 # ---------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock / throttle reasons DURING the timed region: an NVML polling thread (10 ms period), or
+    `nvidia-smi -lms` when pynvml is unavailable."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        self.p = None
+        import threading
+        self.samples, self.reasons, self.power, self.mx = [], set(), [], None
+        self.p = self.f = self.thread = None
+        self._stop = threading.Event()
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
-                                       "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[gpu_index]) if vis and vis.split(",")[gpu_index].strip().isdigit() else gpu_index
+            h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            names = {"hw_slowdown": pynvml.nvmlClocksThrottleReasonHwSlowdown,
+                     "hw_thermal_slowdown": pynvml.nvmlClocksThrottleReasonHwThermalSlowdown,
+                     "sw_thermal_slowdown": pynvml.nvmlClocksThrottleReasonSwThermalSlowdown,
+                     "sw_power_cap": pynvml.nvmlClocksThrottleReasonSwPowerCap}
+
+            def poll():
+                while not self._stop.is_set():
+                    try:
+                        self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                        self.power.append(pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0)
+                        r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                        for k, bit in names.items():
+                            if r & bit:
+                                self.reasons.add(k)
+                    except Exception:
+                        pass
+                    self._stop.wait(0.01)
+            self.thread = threading.Thread(target=poll, daemon=True)
+            self.thread.start()
         except Exception:
-            self.p = None
+            self.thread = None
+            self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+            try:
+                self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
+                                           "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+            except Exception:
+                self.p = None
 
     def stop(self):
         out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
+        if self.thread is not None:
+            self._stop.set()
+            self.thread.join(timeout=2)
+            if self.samples:
+                sm = sorted(self.samples)
+                out.update(sm_mhz=sm[len(sm) // 2], sm_min_mhz=sm[0], sm_max_mhz=self.mx, reasons=sorted(self.reasons),
+                           samples=len(sm), power_w_max=max(self.power) if self.power else None, source="nvml")
+            return out
         if self.p is None:
             return out
         self.p.terminate()
@@ -189,8 +230,8 @@ class ClockSampler:
                     reasons.add(name)
         if sm:
             sm.sort()
-            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm),
-                       power_w_max=max(power))
+            out.update(sm_mhz=sm[len(sm) // 2], sm_min_mhz=sm[0], sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm),
+                       power_w_max=max(power), source="nvidia-smi")
         try:
             os.unlink(self.f.name)
         except OSError:
@@ -314,25 +355,41 @@ def main_ours(args):
         return 0
 
     # ---- roofline of the dominant kernel ------------------------------------------------------
-    peaks = {}
+    # peak = fp32-accurate tensor rate = TF32 dense / 3 (3xTF32), TF32 dense = 1/2 of the bf16 dense rate in
+    # MEASURED_PEAKS.json (sustained figure: the kernel is timed inside a long step).  The cuBLAS TF32 GEMM
+    # rate measured in this run is reported beside it.
+    peaks, peak_src = {}, "of fallback"
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
             peaks = json.load(f)
+        peak_src = "of measured"
     except Exception:
         pass
+    bf16 = float(peaks.get("bf16_tflops_sustained") or peaks.get("bf16_tflops") or 1400.0)
+    peak = bf16 / 2.0 / 3.0
     tf32 = measure_tf32_peak(torch)
     dom = max(("splat_fwd", "splat_bwd"), key=lambda k: kprof.get(k, {}).get("total_ms", 0.0))
     d = kprof.get(dom, {})
     avg_ms = d.get("avg_ms") or float("nan")
     flops_launch = FLOP_PER_EVAL[dom] * float(B) * N * R * R
     achieved = flops_launch / (avg_ms * 1e-3) / 1e12
-    peak = tf32 / 3.0
-    roofline = dict(bound="tensor", kernel=dom, achieved=achieved, peak=peak, unit="TFLOP/s", frac=achieved / peak, traffic=None,
+    traffic = None
+    try:   # dram bytes per launch of this kernel at this shape, from the committed ncu --set full capture
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f).get(f"{dom}:N{N}:R{R}:B{B}")
+        traffic = t["dram_bytes"] if t else None
+    except Exception:
+        pass
+    roofline = dict(bound="tensor", kernel=dom, achieved=achieved, peak=peak, unit="TFLOP/s", frac=achieved / peak, traffic=traffic,
+                    peak_source=f"{peak_src}: bf16 {bf16:.0f} TFLOP/s sustained / 2 (TF32) / 3 (3xTF32)",
+                    cublas_tf32_inrun_tflops=tf32, frac_of_cublas_tf32_over_3=achieved / (tf32 / 3.0),
                     avg_launch_ms=avg_ms, share_of_step=d.get("total_ms", 0.0) / ms_total if ms_total else None,
-                    note=f"algorithmic {FLOP_PER_EVAL[dom]:.0f} FLOP/eval x {B*N*R*R:.3e} evals per launch; peak = cuBLAS TF32 "
-                         f"{tf32:.0f} TFLOP/s measured in this run / 3 (3xTF32 for fp32 accuracy); bf16 peak of measured "
-                         f"{peaks.get('bf16_tflops', 'n/a')} for context; per-kernel ms over the timed region: "
-                         + ", ".join(f"{k}={v['avg_ms']:.3f}x{v['n']}" for k, v in sorted(kprof.items())))
+                    kernels_ms={k: round(v["avg_ms"], 4) for k, v in sorted(kprof.items())},
+                    launches_per_step={k: v["n"] / steps for k, v in sorted(kprof.items())},
+                    note=f"algorithmic {FLOP_PER_EVAL[dom]:.0f} FLOP/eval x {B*N*R*R:.3e} evals per launch (SURVEY 8d); the other tensor kernel: "
+                         + ", ".join(f"{k} {FLOP_PER_EVAL[k] * float(B) * N * R * R / (kprof[k]['avg_ms'] * 1e-3) / 1e12:.0f} TFLOP/s"
+                                     for k in ("splat_fwd", "splat_bwd") if k != dom and k in kprof)
+                         + "; traffic = dram read+write bytes per launch from profiles/ (ncu --set full)")
 
     cpu_baseline = None
     if not args.no_cpu_baseline:
