@@ -392,7 +392,7 @@ def main_ours(args):
                          + "; traffic = dram read+write bytes per launch from profiles/ (ncu --set full)")
 
     cpu_baseline = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:      # reported at N=1 only
         cpu_baseline, _ = run_cpu_sample(N, R, budget_s=args.cpu_seconds)
 
     line = dict(metric=METRIC, value=evals_step / (ms_step * 1e-3), unit=UNIT, n_gpus=world, steps=steps, warmup=warmup,

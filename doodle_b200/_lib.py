@@ -18,7 +18,7 @@ ABI_VERSION = 1
 SPLAT_AUTO, SPLAT_SIMT, SPLAT_TC = 0, 1, 2
 
 EXPORTS = (
-    "helio_abi_version", "helio_last_error", "helio_device_ok", "helio_geom_workspace_bytes", "helio_geom_fwd",
+    "helio_abi_version", "helio_last_error", "helio_device_ok", "helio_set_tc_pair_mode", "helio_geom_workspace_bytes", "helio_geom_fwd",
     "helio_geom_bwd", "helio_splat_fwd", "helio_splat_bwd", "helio_image_max", "helio_loss_fwd", "helio_loss_bwd",
 )
 
@@ -60,6 +60,8 @@ def _declare(lib):
     lib.helio_last_error.argtypes = []
     lib.helio_device_ok.restype = i
     lib.helio_device_ok.argtypes = []
+    lib.helio_set_tc_pair_mode.restype = i
+    lib.helio_set_tc_pair_mode.argtypes = [i]
     lib.helio_geom_workspace_bytes.restype = i64
     lib.helio_geom_workspace_bytes.argtypes = [i, i]
     lib.helio_geom_fwd.restype = i

@@ -1,4 +1,5 @@
 // extern "C" entry points of libhelio_sm100.so (see include/helio_b200.h for the contract).
+#include <atomic>
 #include <cstdlib>
 #include <mutex>
 
@@ -47,16 +48,17 @@ int require_device(const DeviceInfo** out) {
     return 0;
 }
 
-// HELIO_TC_PAIR = 1 forces single-CTA tcgen05 kernels, 2 forces CTA pairs (cta_group::2); default 0 = auto.
-// Debug / A-B switch only; read once.
-int tc_pair_mode() {
-    static const int mode = []() {
+// tcgen05 kernels: 0 = auto (CTA pairs, cta_group::2, where the shape allows), 1 = single-CTA only, 2 = force pairs.
+// Initial value from HELIO_TC_PAIR; helio_set_tc_pair_mode() changes it at run time (A/B tests, parity tests).
+std::atomic<int>& tc_pair_state() {
+    static std::atomic<int> mode{[]() {
         const char* e = std::getenv("HELIO_TC_PAIR");
         const int v = e ? std::atoi(e) : 0;
         return (v == 1 || v == 2) ? v : 0;
-    }();
+    }()};
     return mode;
 }
+int tc_pair_mode() { return tc_pair_state().load(std::memory_order_relaxed); }
 
 inline unsigned geom_blocks(int B, int N) { return (unsigned)(((long long)B * N + kGeomThreads - 1) / kGeomThreads); }
 
@@ -71,6 +73,12 @@ HELIO_API const char* helio_last_error(void) { return last_error_buf(); }
 HELIO_API int helio_device_ok(void) {
     const DeviceInfo* d = nullptr;
     return require_device(&d) == 0 ? 1 : 0;
+}
+
+HELIO_API int helio_set_tc_pair_mode(int mode) {
+    if (mode < 0 || mode > 2) return set_error(HELIO_E_BADARG, "bad argument: %s%s", "tc pair mode must be 0, 1 or 2");
+    tc_pair_state().store(mode, std::memory_order_relaxed);
+    return 0;
 }
 
 HELIO_API int64_t helio_geom_workspace_bytes(int B, int N) {

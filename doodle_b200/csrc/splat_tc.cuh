@@ -477,43 +477,64 @@ splat_bwd_tc_kernel(const float4* __restrict__ params, const float* __restrict__
                         const int k0 = c * C::kKC;
                         float4 vals[8];
                         uint32_t offs[8];
+                        // whole operand tile inside the image: no per-element bounds checks (the common case)
+                        const bool inside = vec && k0 + C::kKC <= R && pbk * NT + row_base + C::kBRows <= R;
                         if (prod == 0) {
                             // operand row = image row i (accumulator column), K = image column j:
                             // 8 lanes cover one 128-byte row segment, a warp instruction covers 4 rows
+                            const int row0 = gw * 32 + (lane >> 3), ch = lane & 7;
+                            if (inside) {
+                                const float4* src = reinterpret_cast<const float4*>(gb + (size_t)(pbk * NT + row_base + row0) * R + k0) + ch;
 #pragma unroll
-                            for (int q = 0; q < 8; ++q) {
-                                const int row = gw * 32 + q * 4 + (lane >> 3), ch = lane & 7;
-                                const int i = pbk * NT + row_base + row, j = k0 + ch * 4;
-                                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                                if (i < R) {
-                                    const float* src = gb + (size_t)i * R + j;
-                                    if (vec && j + 3 < R) {
-                                        v = __ldg(reinterpret_cast<const float4*>(src));
-                                    } else {
-                                        if (j < R) v.x = __ldg(src);
-                                        if (j + 1 < R) v.y = __ldg(src + 1);
-                                        if (j + 2 < R) v.z = __ldg(src + 2);
-                                        if (j + 3 < R) v.w = __ldg(src + 3);
+                                for (int q = 0; q < 8; ++q) vals[q] = __ldg(src + (size_t)q * R);   // 4 rows = R float4
+                            } else {
+#pragma unroll
+                                for (int q = 0; q < 8; ++q) {
+                                    const int i = pbk * NT + row_base + row0 + q * 4, j = k0 + ch * 4;
+                                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                                    if (i < R) {
+                                        const float* src = gb + (size_t)i * R + j;
+                                        if (vec && j + 3 < R) {
+                                            v = __ldg(reinterpret_cast<const float4*>(src));
+                                        } else {
+                                            if (j < R) v.x = __ldg(src);
+                                            if (j + 1 < R) v.y = __ldg(src + 1);
+                                            if (j + 2 < R) v.z = __ldg(src + 2);
+                                            if (j + 3 < R) v.w = __ldg(src + 3);
+                                        }
                                     }
+                                    vals[q] = v;
                                 }
-                                vals[q] = v;
-                                offs[q] = tc::sw128_offset((uint32_t)row, (uint32_t)ch);
                             }
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) offs[q] = tc::sw128_offset((uint32_t)(row0 + q * 4), (uint32_t)ch);
                         } else {
                             // operand row = image column j (accumulator column), K = image row i:
                             // lanes read consecutive columns of one image row (coalesced), transposing in registers
                             const int j = pbk * NT + row_base + t;
+                            if (inside) {
+                                const float* src = gb + (size_t)k0 * R + j;
 #pragma unroll
-                            for (int q = 0; q < 8; ++q) {
-                                float x[4];
-#pragma unroll
-                                for (int e = 0; e < 4; ++e) {
-                                    const int i = k0 + 4 * q + e;
-                                    x[e] = (i < R && j < R) ? __ldg(gb + (size_t)i * R + j) : 0.f;
+                                for (int q = 0; q < 8; ++q) {
+                                    vals[q].x = __ldg(src + (size_t)(4 * q) * R);
+                                    vals[q].y = __ldg(src + (size_t)(4 * q + 1) * R);
+                                    vals[q].z = __ldg(src + (size_t)(4 * q + 2) * R);
+                                    vals[q].w = __ldg(src + (size_t)(4 * q + 3) * R);
                                 }
-                                vals[q] = make_float4(x[0], x[1], x[2], x[3]);
-                                offs[q] = tc::sw128_offset((uint32_t)t, (uint32_t)q);
+                            } else {
+#pragma unroll
+                                for (int q = 0; q < 8; ++q) {
+                                    float x[4];
+#pragma unroll
+                                    for (int e = 0; e < 4; ++e) {
+                                        const int i = k0 + 4 * q + e;
+                                        x[e] = (i < R && j < R) ? __ldg(gb + (size_t)i * R + j) : 0.f;
+                                    }
+                                    vals[q] = make_float4(x[0], x[1], x[2], x[3]);
+                                }
                             }
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) offs[q] = tc::sw128_offset((uint32_t)t, (uint32_t)q);
                         }
                         cx.producer_acquire(s, (it / C::kStages) & 1);
                         const uint32_t hi_base = cx.smem_u + (uint32_t)(s * C::kStageBytes + 2 * C::kABytes);
@@ -588,10 +609,11 @@ splat_bwd_tc_kernel(const float4* __restrict__ params, const float* __restrict__
                             for (int e = 0; e < 4; ++e) {
                                 // columns >= R hold exact zeros (their operand rows are zero)
                                 const float d = x[e] - ctr;
-                                const float w = ex2((d * nk2) * d) * v[e4 + e];
+                                const float dd = d * d;
+                                const float w = ex2(dd * nk2) * v[e4 + e];
                                 s0 += w;
                                 s1 = fmaf(w, d, s1);
-                                s2 = fmaf(w * d, d, s2);
+                                s2 = fmaf(w, dd, s2);
                             }
                         }
                     }

@@ -66,6 +66,11 @@ HELIO_API const char* helio_last_error(void);
 /* 1 if the current device can run the kernels (cc 10.x), else 0 (and last_error is set). */
 HELIO_API int helio_device_ok(void);
 
+/* tcgen05 splat kernels: 0 = auto (CTA pairs / cta_group::2 where the shape allows; default), 1 = single-CTA
+ * kernels only, 2 = force CTA pairs.  Process-wide; initial value from the environment variable HELIO_TC_PAIR.
+ * No reference counterpart (tuning / A-B switch of this library). */
+HELIO_API int helio_set_tc_pair_mode(int mode);
+
 /* Bytes of workspace helio_geom_fwd needs for (B, N) (block partials + ticket counter).  The
  * workspace must be zero-initialised ONCE by the caller; the kernel leaves it zeroed. */
 HELIO_API int64_t helio_geom_workspace_bytes(int B, int N);
