@@ -39,13 +39,14 @@ constexpr int kTcMaxR = 1024;  // coordinate tables live in shared memory
 // ------------------------------------------------------------------------------------------------
 // pieces shared by both kernels
 // ------------------------------------------------------------------------------------------------
-template <int NT, int CG, int BROWS>
+template <int NT, int CG, int BROWS, int ASPLIT>
 struct SplatTcLayout {
     static constexpr int kNT = NT;                       // UMMA N (accumulator columns)
     static constexpr int kM = 128;                       // A rows per CTA = TMEM lanes
     static constexpr int kBRows = BROWS;                 // B operand rows produced by each CTA (NT / CG)
     static constexpr int kKC = 32;                       // K per stage (one 128-byte swizzle row of tf32)
-    static constexpr int kAWarps = kM / 32;
+    static constexpr int kASplit = ASPLIT;               // warps sharing one 32-row slab of A (each takes kKC / ASPLIT of K)
+    static constexpr int kAWarps = kM / 32 * ASPLIT;
     static constexpr int kBWarps = kBRows / 32;
     static constexpr int kMmaWarp = kAWarps + kBWarps;
     static constexpr int kEpiWarp0 = kMmaWarp + 1;
@@ -201,7 +202,7 @@ struct SplatTcCtx {
 // forward
 // ================================================================================================
 template <int NT, int CG>
-using SplatFwdTc = SplatTcLayout<NT, CG, NT / CG>;
+using SplatFwdTc = SplatTcLayout<NT, CG, NT / CG, 1>;
 
 // Producer mapping: a warp owns 32 operand rows (image rows for A, image columns for B); a lane owns
 // 4 consecutive heliostats of the stage (one 16-byte chunk of the K-major row) and walks 8 of the
@@ -226,6 +227,7 @@ splat_fwd_tc_kernel(const float4* __restrict__ params, float* __restrict__ img, 
         // ================= producers =================
         // lane = (row subgroup rs = lane >> 3, K chunk ch = lane & 7): per step a warp covers 4 operand rows x
         // 32 heliostats, each lane evaluating its 4 heliostats for one row and storing them as one 16-byte chunk.
+        static_assert(C::kASplit == 1, "forward producers take whole K stages");
         const bool isA = warp < C::kAWarps;
         const int wrow = (isA ? warp : warp - C::kAWarps) * 32;          // first operand row of this warp (CTA-local)
         const int rs = lane >> 3, ch = lane & 7;
@@ -252,13 +254,15 @@ splat_fwd_tc_kernel(const float4* __restrict__ params, float* __restrict__ img, 
             };
             prefetch(0);
             for (int c = 0; c < nchunks; ++c, ++it) {
-                float ctr[4], nk2[4], scl[4];
+                float ctr[4], nk2[4], la[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     const bool have = c * C::kKC + 4 * ch + e < N;
                     ctr[e] = isA ? pr[e].x : pr[e].y;
                     nk2[e] = -pr[e].z;
-                    scl[e] = have ? (isA ? pr[e].w : 1.f) : 0.f;           // K padding: exact zeros
+                    // amplitude folded into the exponent (amp ~ 1: lg2.approx is exact to 2^-22 absolute there);
+                    // K padding: 2^-inf = exact zeros
+                    la[e] = have ? (isA ? __log2f(pr[e].w) : 0.f) : -INFINITY;
                 }
                 prefetch(c + 1 < nchunks ? c + 1 : c);
                 const int s = it % C::kStages;
@@ -270,7 +274,7 @@ splat_fwd_tc_kernel(const float4* __restrict__ params, float* __restrict__ img, 
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         const float d = xr[st] - ctr[e];
-                        const float v = ex2((d * nk2[e]) * d) * scl[e];
+                        const float v = ex2(fmaf(d * nk2[e], d, la[e]));
                         tc::split_tf32(v, hi[e], lo[e]);
                     }
                     const uint32_t dst = base + (uint32_t)(st >> 1) * 1024u + ((st & 1) ? off_odd : off_even);
@@ -394,7 +398,7 @@ inline cudaError_t splat_tc_fwd(const float* params, float* img, int B, int N, i
 // The epilogue thread that owns TMEM lane n keeps {S0,Sx,Sxx} from product 0 in registers, adds
 // {Sy,Syy} from product 1 and writes one float4 per heliostat.
 template <int NT, int CG>
-using SplatBwdTc = SplatTcLayout<NT, CG, NT / CG>;
+using SplatBwdTc = SplatTcLayout<NT, CG, NT / CG, 2>;
 
 template <int NT, int CG>
 __global__ void __launch_bounds__(SplatBwdTc<NT, CG>::kThreads, 1)
@@ -413,43 +417,47 @@ splat_bwd_tc_kernel(const float4* __restrict__ params, const float* __restrict__
     constexpr int kTileH = C::kM * CG;               // heliostats per tile
 
     if (warp < C::kAWarps) {
-        // ================= Gaussian operand: thread = heliostat row =================
-        const int r = threadIdx.x;
+        // ================= Gaussian operand: thread = heliostat row, warp = (32-row slab, K slice) =================
+        // kASplit warps share a slab and each generates kKC / kASplit of the stage's K range, which halves the
+        // per-stage latency of a producer warp (the critical path of this kernel).  K padding (k >= R) needs no
+        // zeroing here: the matching rows of the gradient operand are exact zeros and these values are finite.
+        constexpr int kQ = 8 / C::kASplit;               // 16-byte chunks of the 128-byte row per warp
+        const int r = (warp % (C::kM / 32)) * 32 + lane;
+        const int q0 = (warp / (C::kM / 32)) * kQ;
         uint32_t it = 0;
         for (int tile = group; tile < num_tiles; tile += ngroups) {
             const int b = tile / nblocks, nb = tile % nblocks;
             const int n = nb * kTileH + (int)cx.rank * C::kM + r;
             const bool live = n < N;
-            const float4 p = live ? __ldg(params + (size_t)b * N + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 p = live ? __ldg(params + (size_t)b * N + n) : make_float4(0.f, 0.f, 0.f, 1.f);
             const float nk2 = -p.z;
+            const float dead = live ? 0.f : -INFINITY;   // rows beyond N: 2^-inf = 0
 #pragma unroll 1
             for (int prod = 0; prod < 2; ++prod) {
                 const float ctr = prod == 0 ? p.y : p.x;
-                const float scale = live ? (prod == 0 ? 1.f : p.w) : 0.f;
-                const uint32_t tab = prod == 0 ? cx.sY_u : cx.sX_u;
+                const float la = dead + (prod == 0 ? 0.f : log2f(p.w));       // amplitude folded into the exponent
+                const uint32_t tab = (prod == 0 ? cx.sY_u : cx.sX_u) + (uint32_t)q0 * 16u;
 #pragma unroll 1
                 for (int pbk = 0; pbk < pblocks; ++pbk) {
 #pragma unroll 1
                     for (int c = 0; c < kchunks; ++c, ++it) {
                         const int s = it % C::kStages;
                         const int k0 = c * C::kKC;
-                        const bool tail = k0 + C::kKC > R;                      // warp-uniform: only the last chunk of a ragged R
                         cx.producer_acquire(s, (it / C::kStages) & 1);
                         const uint32_t hi_base = cx.smem_u + (uint32_t)(s * C::kStageBytes);
                         const uint32_t lo_base = hi_base + C::kABytes;
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) {
+                        for (int q = 0; q < kQ; ++q) {
                             const float4 xs = tc::lds_v4(tab + (uint32_t)(k0 + 4 * q) * 4u);
                             const float x[4] = {xs.x, xs.y, xs.z, xs.w};
                             float hi[4], lo[4];
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
                                 const float d = x[e] - ctr;
-                                float v = ex2((d * nk2) * d) * scale;
-                                if (tail && k0 + 4 * q + e >= R) v = 0.f;       // K padding: exact zeros
+                                const float v = ex2(fmaf(d * nk2, d, la));
                                 tc::split_tf32(v, hi[e], lo[e]);
                             }
-                            const uint32_t off = tc::sw128_offset((uint32_t)r, (uint32_t)q);
+                            const uint32_t off = tc::sw128_offset((uint32_t)r, (uint32_t)(q0 + q));
                             tc::sts_v4(hi_base + off, hi[0], hi[1], hi[2], hi[3]);
                             tc::sts_v4(lo_base + off, lo[0], lo[1], lo[2], lo[3]);
                         }
