@@ -172,8 +172,10 @@ struct SplatTcCtx {
             const uint64_t ko = (uint64_t)(k * 32 >> 4);   // +32 bytes per K step of 8 tf32
             if constexpr (CG == 2) {
                 tc::mma_tf32_ss_2cta(d_tmem, a_hi + ko, b_hi + ko, idesc, !(first && k == 0));
+#ifndef HELIO_DEBUG_1XTF32   // timing experiment only: results are wrong without the cross terms
                 tc::mma_tf32_ss_2cta(d_tmem, a_hi + ko, b_lo + ko, idesc, 1);
                 tc::mma_tf32_ss_2cta(d_tmem, a_lo + ko, b_hi + ko, idesc, 1);
+#endif
             } else {
                 tc::mma_tf32_ss(d_tmem, a_hi + ko, b_hi + ko, idesc, !(first && k == 0));
                 tc::mma_tf32_ss(d_tmem, a_hi + ko, b_lo + ko, idesc, 1);
@@ -295,7 +297,7 @@ splat_fwd_tc_kernel(const float4* __restrict__ params, float* __restrict__ img, 
                 for (int c = 0; c < nchunks; ++c, ++it) {
                     const int s = it % C::kStages;
                     cx.mma_wait_full(s, (it / C::kStages) & 1);
-                    if (lane == 0) cx.issue_stage(s, d_tmem, c == 0, c == nchunks - 1, acc);
+                    if (tc::elect_one()) cx.issue_stage(s, d_tmem, c == 0, c == nchunks - 1, acc);
                     __syncwarp();
                 }
             }
@@ -575,7 +577,7 @@ splat_bwd_tc_kernel(const float4* __restrict__ params, const float* __restrict__
                     for (int c = 0; c < kchunks; ++c, ++it) {
                         const int s = it % C::kStages;
                         cx.mma_wait_full(s, (it / C::kStages) & 1);
-                        if (lane == 0) cx.issue_stage(s, d_tmem, c == 0, c == kchunks - 1, acc);
+                        if (tc::elect_one()) cx.issue_stage(s, d_tmem, c == 0, c == kchunks - 1, acc);
                         __syncwarp();
                     }
                 }
