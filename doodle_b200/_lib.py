@@ -13,13 +13,14 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libhelio_sm100.so")
 CSRC = os.path.join(_HERE, "csrc")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 SPLAT_AUTO, SPLAT_SIMT, SPLAT_TC = 0, 1, 2
 
 EXPORTS = (
     "helio_abi_version", "helio_last_error", "helio_device_ok", "helio_set_tc_pair_mode", "helio_geom_workspace_bytes", "helio_geom_fwd",
     "helio_geom_bwd", "helio_splat_fwd", "helio_splat_bwd", "helio_image_max", "helio_loss_fwd", "helio_loss_bwd",
+    "helio_loss_bwd_packed", "helio_loss_pack", "helio_step_fwd", "helio_step_bwd",
 )
 
 
@@ -78,6 +79,14 @@ def _declare(lib):
     lib.helio_loss_fwd.argtypes = [p, p, p, p, i, i, p, p]
     lib.helio_loss_bwd.restype = i
     lib.helio_loss_bwd.argtypes = [p, p, p, p, p, p, i, i, p, p]
+    lib.helio_loss_bwd_packed.restype = i
+    lib.helio_loss_bwd_packed.argtypes = [p, p, p, p, p, p, p, i, i, p, p]
+    lib.helio_loss_pack.restype = i
+    lib.helio_loss_pack.argtypes = [p, i, p, p]
+    lib.helio_step_fwd.restype = i
+    lib.helio_step_fwd.argtypes = [sp, p, p, p, p, p, i, i, i, i, i] + [p] * 14 + [p, i64, p]
+    lib.helio_step_bwd.restype = i
+    lib.helio_step_bwd.argtypes = [sp] + [p] * 9 + [i, i, i, i] + [p] * 7 + [p, p, p, p]
 
 
 def load(build_if_missing: bool = False):

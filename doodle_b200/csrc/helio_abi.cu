@@ -160,8 +160,8 @@ HELIO_API int helio_image_max(const float* target, int B, int R, float* tx, void
     if (int rc = require_device(&d)) return rc;
     HELIO_REQUIRE(target && tx, "null pointer");
     HELIO_REQUIRE(B > 0 && R > 0, "B, R must be positive");
-    image_max_kernel<<<B, kLossThreads, 0, (cudaStream_t)stream>>>(target, R, tx);
-    HELIO_CUDA_OK(cudaGetLastError());
+    const int slices = loss_slices(B, R, d->sms);
+    HELIO_CUDA_OK(launch_image_clusters(image_max_kernel, B, slices, (cudaStream_t)stream, target, R, slices, tx));
     return 0;
 }
 
@@ -171,16 +171,23 @@ HELIO_API int helio_loss_fwd(const float* img, const float* target, const float*
     if (int rc = require_device(&d)) return rc;
     HELIO_REQUIRE(img && target && dmaps && tx && per_img, "null pointer");
     HELIO_REQUIRE(B > 0 && R > 0, "B, R must be positive");
-    loss_fwd_kernel<<<B, kLossThreads, 0, (cudaStream_t)stream>>>(img, target, dmaps, tx, R, per_img);
-    HELIO_CUDA_OK(cudaGetLastError());
+    const int slices = loss_slices(B, R, d->sms);
+    HELIO_CUDA_OK(launch_image_clusters(loss_fwd_kernel, B, slices, (cudaStream_t)stream, img, target, dmaps, tx, R, slices, per_img));
     return 0;
 }
 
 HELIO_API int helio_loss_bwd(const float* img, const float* target, const float* dmaps, const float* tx, const float* g_per_img,
                    const float* g_img_in, int B, int R, float* g_img, void* stream) {
+    HELIO_REQUIRE(g_per_img, "null pointer");
+    return helio_loss_bwd_packed(img, target, dmaps, tx, g_per_img, nullptr, g_img_in, B, R, g_img, stream);
+}
+
+HELIO_API int helio_loss_bwd_packed(const float* img, const float* target, const float* dmaps, const float* tx,
+                          const float* g_per_img, const float* g_packed, const float* g_img_in, int B, int R, float* g_img,
+                          void* stream) {
     const DeviceInfo* d = nullptr;
     if (int rc = require_device(&d)) return rc;
-    HELIO_REQUIRE(img && target && dmaps && tx && g_per_img && g_img, "null pointer");
+    HELIO_REQUIRE(img && target && dmaps && tx && (g_per_img || g_packed) && g_img, "null pointer");
     HELIO_REQUIRE(B > 0 && R > 0, "B, R must be positive");
     // enough CTAs to fill the machine even for small B
     const size_t vecs = ((size_t)R * R + 3) / 4;
@@ -189,9 +196,63 @@ HELIO_API int helio_loss_bwd(const float* img, const float* target, const float*
     if (slices > want) slices = want;
     if (slices < 1) slices = 1;
     loss_bwd_kernel<<<(unsigned)((long long)B * slices), kLossThreads, 0, (cudaStream_t)stream>>>(
-        img, target, dmaps, tx, g_per_img, g_img_in, R, slices, g_img);
+        img, target, dmaps, tx, g_per_img, g_packed, g_img_in, R, slices, g_img);
     HELIO_CUDA_OK(cudaGetLastError());
     return 0;
+}
+
+HELIO_API int helio_loss_pack(const float* per_img, int B, float* packed, void* stream) {
+    const DeviceInfo* d = nullptr;
+    if (int rc = require_device(&d)) return rc;
+    HELIO_REQUIRE(per_img && packed, "null pointer");
+    HELIO_REQUIRE(B > 0, "B must be positive");
+    loss_pack_kernel<<<1, kLossThreads, 0, (cudaStream_t)stream>>>(per_img, B, packed);
+    HELIO_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+HELIO_API int helio_step_fwd(const helio_scene_t* scene, const float* helio_pos, const float* sun, const float* action,
+                   const float* errs, const float* dmaps, int B, int N, int R, int impl, int render_target, float* params,
+                   float* actual, float* refl, float* ideal, float* bounds, float* angles, float* img, float* target,
+                   float* tx, float* per_img, float* packed, float* tgt_params, float* tgt_actual, float* tgt_refl,
+                   void* workspace, int64_t workspace_bytes, void* stream) {
+    HELIO_REQUIRE(scene && ideal && bounds && angles && img && target && tx && per_img && packed && dmaps, "null pointer");
+    HELIO_REQUIRE(R > 0, "R must be positive");
+    // noisy field: K1 (with ideal normals, boundary, alignment and their sums -> packed[2..3]) + K2
+    if (int rc = helio_geom_fwd(scene, helio_pos, sun, action, errs, B, N, params, actual, refl, ideal, bounds, angles,
+                                packed + 2, workspace, workspace_bytes, stream)) return rc;
+    if (int rc = helio_splat_fwd(params, B, N, R, scene->width, scene->height, img, impl, stream)) return rc;
+    if (render_target) {
+        // error-free field aimed with the ideal normals (test_environment.py:429-436)
+        HELIO_REQUIRE(tgt_params && tgt_actual && tgt_refl, "target render needs scratch buffers");
+        if (int rc = helio_geom_fwd(scene, helio_pos, sun, ideal, nullptr, B, N, tgt_params, tgt_actual, tgt_refl, nullptr,
+                                    nullptr, nullptr, nullptr, nullptr, 0, stream)) return rc;
+        if (int rc = helio_splat_fwd(tgt_params, B, N, R, scene->width, scene->height, target, impl, stream)) return rc;
+        if (int rc = helio_image_max(target, B, R, tx, stream)) return rc;
+    }
+    if (int rc = helio_loss_fwd(img, target, dmaps, tx, B, R, per_img, stream)) return rc;
+    return helio_loss_pack(per_img, B, packed, stream);
+}
+
+HELIO_API int helio_step_bwd(const helio_scene_t* scene, const float* helio_pos, const float* sun, const float* action,
+                   const float* errs, const float* params, const float* img, const float* target, const float* dmaps,
+                   const float* tx, int B, int N, int R, int impl, const float* g_packed, const float* g_per_img,
+                   const float* g_img_in, const float* g_actual, const float* g_refl, const float* g_bounds,
+                   const float* g_angles, float* g_img, float* moments, float* g_action, void* stream) {
+    HELIO_REQUIRE(scene && params, "null pointer");
+    HELIO_REQUIRE(moments || !(g_packed || g_per_img || g_img_in), "moments scratch missing");
+    const float* g_mom = nullptr;
+    if (g_packed || g_per_img) {
+        HELIO_REQUIRE(g_img, "g_img scratch missing");
+        if (int rc = helio_loss_bwd_packed(img, target, dmaps, tx, g_per_img, g_packed, g_img_in, B, R, g_img, stream)) return rc;
+        if (int rc = helio_splat_bwd(params, g_img, B, N, R, scene->width, scene->height, moments, impl, stream)) return rc;
+        g_mom = moments;
+    } else if (g_img_in) {
+        if (int rc = helio_splat_bwd(params, g_img_in, B, N, R, scene->width, scene->height, moments, impl, stream)) return rc;
+        g_mom = moments;
+    }
+    return helio_geom_bwd(scene, helio_pos, sun, action, errs, B, N, g_mom, g_actual, g_refl, g_bounds, g_angles,
+                          g_packed ? g_packed + 2 : nullptr, g_action, stream);
 }
 
 }  // extern "C"

@@ -10,6 +10,9 @@ Differences, all opt-in or bug-compatible:
   * ``new_sun_pos_every_reset=True`` works (the reference calls a method that does not exist,
     test_environment.py:379);
   * the six NaN/Inf asserts (test_environment.py:495-501) read ONE fused device flag (one sync);
+  * ``fused_step`` (keyword-only, default True): ``step`` runs as one C-ABI call forward and one backward
+    (helio_step_fwd / helio_step_bwd: the same kernels, far less host time for small fields); the
+    error-mask and exponential-risk variants take the composed path;
   * ``cache_target`` (keyword-only extension, default False = re-render the target every step as
     the reference does, test_environment.py:429-435).  The target only depends on ``sun_pos``, so
     caching it is exact.
@@ -17,6 +20,7 @@ Differences, all opt-in or bug-compatible:
 from __future__ import annotations
 
 import math
+from types import SimpleNamespace
 
 import numpy as np
 import torch
@@ -24,7 +28,7 @@ import torch.nn.functional as F
 from scipy.ndimage import distance_transform_edt
 
 from .field import HelioField
-from .functional import ImageLossFn, image_max, require_cuda
+from .functional import ImageLossFn, StepFn, _cf, image_max, require_cuda
 
 try:  # gymnasium is optional: only Env / spaces.Box / spaces.Dict are touched (test_environment.py:11-12)
     import gymnasium as gym
@@ -121,6 +125,7 @@ class HelioEnv(_EnvBase):
                  *,
                  cache_target=False,
                  check_finite=True,
+                 fused_step=True,
                  ):
         super().__init__()
         require_cuda(torch.device(device), "HelioEnv")
@@ -153,6 +158,7 @@ class HelioEnv(_EnvBase):
         self.single_sun = single_sun
         self.cache_target = cache_target
         self.check_finite = check_finite
+        self.fused_step = fused_step
         self._target_cache = None
 
         action_dim = heliostat_pos.shape[0] * 3
@@ -260,27 +266,41 @@ class HelioEnv(_EnvBase):
             action = torch.tensor(action, dtype=torch.float32, device=self.device)
         B, N, R = self.batch_size, self.num_heliostats, self.resolution
 
-        out = self.noisy_field._render_full(self.sun_pos, action, want_aux=True)     # K1 + K2
-        img, ideal_normals = out.img, out.ideal
+        if self.fused_step and not self.use_error_mask and not self.exponential_risk:
+            nf = self.noisy_field
+            act = action.to(device=nf.device, dtype=torch.float32)
+            normals = act.reshape(B, N, 3).contiguous()
+            cached = self._target_cache if self.cache_target and self._target_cache is not None else (None, None)
+            img, packed, _actual, refl, ideal_normals, bounds, angles, per_img, target, tx = StepFn.apply(
+                normals, self.sun_pos, _cf(nf._select_errors(B)), nf.heliostat_positions, self.distance_maps, nf.scene(),
+                nf._geom_workspace(B), R, nf.splat_impl, nf.splat_impl if nf.splat_impl_bwd is None else nf.splat_impl_bwd,
+                cached[0], cached[1])
+            if self.cache_target and self._target_cache is None:
+                self._target_cache = (target, tx)
+            out = SimpleNamespace(refl=refl, bounds=bounds, angles=angles)
+        else:
+            out = self.noisy_field._render_full(self.sun_pos, action, want_aux=True)     # K1 + K2
+            img, ideal_normals = out.img, out.ideal
+            target, tx = self._target(ideal_normals)
+            per_img = ImageLossFn.apply(img, target, self.distance_maps, tx)             # K4: [B,3]
+            packed = None
         aux = torch.cat([self.sun_pos.detach(), action.flatten(1)], dim=1)
-
-        target, tx = self._target(ideal_normals)
-        per_img = ImageLossFn.apply(img, target, self.distance_maps, tx)             # K4: [B,3]
         avg_error_per_heatmap = per_img[:, 2] / float(R * R)
-        if self.use_error_mask:                                                      # :445-452
-            cutoff = self._quantile_cutoff(avg_error_per_heatmap)
-            mask = (avg_error_per_heatmap > cutoff).float()
-            sq, ds = per_img[:, 0] * mask, per_img[:, 1] * mask
-        else:
-            sq, ds = per_img[:, 0], per_img[:, 1]
 
-        if not self.exponential_risk:                                                # :464-480
-            bound_sum = out.sums[0]
-        else:
-            bound_sum = torch.exp(out.bounds + 1e-6).sum()
-        packed = torch.stack([sq.sum(), ds.sum(), bound_sum, out.sums[1]])
+        if packed is None:
+            if self.use_error_mask:                                                      # :445-452
+                cutoff = self._quantile_cutoff(avg_error_per_heatmap)
+                mask = (avg_error_per_heatmap > cutoff).float()
+                sq, ds = per_img[:, 0] * mask, per_img[:, 1] * mask
+            else:
+                sq, ds = per_img[:, 0], per_img[:, 1]
+            if not self.exponential_risk:                                                # :464-480
+                bound_sum = out.sums[0]
+            else:
+                bound_sum = torch.exp(out.bounds + 1e-6).sum()
+            packed = torch.stack([sq.sum(), ds.sum(), bound_sum, out.sums[1]])
         means = self._reduce_means(packed)
-        mse, dist_l, bound, alignment_loss = means[0], means[1], means[2], means[3]
+        mse, dist_l, bound, alignment_loss = means.unbind(0)
 
         if self.check_finite:                                                        # :495-501, one sync
             if not bool(torch.isfinite(means[:3]).all()):

@@ -52,14 +52,19 @@ def collect_profile():
 
 
 class _Call:
-    """Context manager around one C-ABI launch: device guard, launch count, optional CUDA events."""
+    """Context manager around one C-ABI launch: device guard (only when the tensors live on another
+    device than the current one), launch count, optional CUDA events."""
+
+    __slots__ = ("name", "guard", "e0")
 
     def __init__(self, name: str, device: torch.device):
-        self.name, self.guard = name, torch.cuda.device(device)
+        self.name = name
+        self.guard = None if device.index is None or device.index == torch._C._cuda_getDevice() else torch.cuda.device(device)
 
     def __enter__(self):
         global _LAUNCHES
-        self.guard.__enter__()
+        if self.guard is not None:
+            self.guard.__enter__()
         _LAUNCHES += 1
         if _PROFILE["on"]:
             self.e0 = torch.cuda.Event(enable_timing=True)
@@ -71,15 +76,19 @@ class _Call:
             e1 = torch.cuda.Event(enable_timing=True)
             e1.record()
             _PROFILE["events"].append((self.name, self.e0, e1))
-        return self.guard.__exit__(*exc)
+        if self.guard is not None:
+            return self.guard.__exit__(*exc)
+        return False
 
 
 def _ptr(t: Optional[torch.Tensor]):
-    return None if t is None else C.c_void_p(t.data_ptr())
+    return None if t is None else t.data_ptr()      # ctypes converts int -> c_void_p for declared argtypes
 
 
 def _stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    """cudaStream_t of torch's current stream on the current device (raw handle: the Python Stream object costs
+    ~20 us to build, which is most of a small field's step)."""
+    return torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice())
 
 
 def _cf(t: torch.Tensor) -> torch.Tensor:
@@ -209,3 +218,72 @@ class ImageLossFn(torch.autograd.Function):
                                     _ptr(g_img), _stream())
         _lib.check(rc, "helio_loss_bwd")
         return g_img, None, None, None
+
+
+class StepFn(torch.autograd.Function):
+    """Whole HelioEnv.step forward / backward as ONE C-ABI call each (helio_step_fwd / helio_step_bwd).
+
+    Same kernels and results as GeomFn -> SplatFn -> ImageLossFn composed by autograd; what it saves is
+    host time (three Function nodes, ~25 small torch ops, 9 ctypes calls per step), which is all a small
+    field costs (N=50, R=128, B=25: the kernels take a few microseconds).
+
+    forward(action[B,N,3], sun, errs, helio, dmaps, scene, workspace, R, impl, impl_bwd, target, tx)
+      -> img, packed[4] = {sum diff^2, sum |diff| dmaps, sum bounds, sum angles}, actual, refl, ideal,
+         bounds, angles, per_img[B,3], target, tx
+    ``target``/``tx`` None = render the target here (test_environment.py:429-436); else reuse them.
+    """
+
+    @staticmethod
+    def forward(ctx, action, sun, errs, helio, dmaps, scene, workspace, R: int, impl: int, impl_bwd: int, target, tx):
+        lib = _lib.load()
+        B, N = sun.shape[0], helio.shape[0]
+        dev = action.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        render_target = target is None
+        params = torch.empty(B, N, 4, **f32)
+        actual, refl, ideal = torch.empty(B, N, 3, **f32), torch.empty(B * N, 3, **f32), torch.empty(B, N, 3, **f32)
+        bounds, angles = torch.empty(B, N, **f32), torch.empty(B, N, **f32)
+        img = torch.empty(B, R, R, **f32)
+        per_img, packed = torch.empty(B, 3, **f32), torch.empty(4, **f32)
+        scratch = None
+        if render_target:
+            target, tx = torch.empty(B, R, R, **f32), torch.empty(B, **f32)
+            scratch = torch.empty(B * N * 10, **f32)     # params, actual, refl of the target render (discarded)
+        with _Call("step_fwd", dev):
+            rc = lib.helio_step_fwd(
+                C.byref(scene), _ptr(helio), _ptr(sun), _ptr(action), _ptr(errs), _ptr(dmaps), B, N, R, impl,
+                1 if render_target else 0, _ptr(params), _ptr(actual), _ptr(refl), _ptr(ideal), _ptr(bounds), _ptr(angles),
+                _ptr(img), _ptr(target), _ptr(tx), _ptr(per_img), _ptr(packed),
+                _ptr(scratch), _ptr(scratch[4 * B * N:]) if render_target else None,
+                _ptr(scratch[7 * B * N:]) if render_target else None,
+                _ptr(workspace), workspace.numel() * workspace.element_size(), _stream())
+        _lib.check(rc, "helio_step_fwd")
+        global _LAUNCHES
+        _LAUNCHES += 6 if render_target else 3       # 7 / 4 kernels enqueued by the call, minus the one _Call counted
+        ctx.save_for_backward(action, sun, errs, helio, dmaps, params, img, target, tx)
+        ctx.cfg = (scene, R, impl_bwd)
+        ctx.set_materialize_grads(False)
+        ctx.mark_non_differentiable(ideal, target, tx)
+        return img, packed, actual, refl, ideal, bounds, angles, per_img, target, tx
+
+    @staticmethod
+    def backward(ctx, g_img_in, g_packed, g_actual, g_refl, g_ideal, g_bounds, g_angles, g_per_img, g_target, g_tx):
+        lib = _lib.load()
+        action, sun, errs, helio, dmaps, params, img, target, tx = ctx.saved_tensors
+        scene, R, impl = ctx.cfg
+        B, N = sun.shape[0], helio.shape[0]
+        gs = [None if g is None else _cf(g) for g in (g_packed, g_per_img, g_img_in, g_actual, g_refl, g_bounds, g_angles)]
+        need_img = gs[0] is not None or gs[1] is not None
+        need_splat = need_img or gs[2] is not None
+        g_action = torch.empty_like(action)
+        g_img = torch.empty_like(img) if need_img else None
+        moments = torch.empty_like(params) if need_splat else None
+        with _Call("step_bwd", action.device):
+            rc = lib.helio_step_bwd(
+                C.byref(scene), _ptr(helio), _ptr(sun), _ptr(action), _ptr(errs), _ptr(params), _ptr(img), _ptr(target),
+                _ptr(dmaps), _ptr(tx), B, N, R, impl, *[_ptr(g) for g in gs],
+                _ptr(g_img), _ptr(moments), _ptr(g_action), _stream())
+        _lib.check(rc, "helio_step_bwd")
+        global _LAUNCHES
+        _LAUNCHES += (1 if need_img else 0) + (1 if need_splat else 0)
+        return (g_action,) + (None,) * 11

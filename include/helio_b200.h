@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define HELIO_ABI_VERSION 1
+#define HELIO_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define HELIO_API __attribute__((visibility("default")))
@@ -137,6 +137,48 @@ HELIO_API int helio_loss_fwd(const float* img, const float* target, const float*
 HELIO_API int helio_loss_bwd(const float* img, const float* target, const float* dmaps, const float* tx,
                    const float* g_per_img, const float* g_img_in, int B, int R, float* g_img,
                    void* stream);
+
+/* helio_loss_bwd with the batch-wide gradients folded in: {g0,g1,g2} = g_per_img[b] (may be NULL) +
+ * {g_packed[0], g_packed[1], 0} (may be NULL), where g_packed[4] (device) are the upstream grads of
+ * helio_step_fwd's packed sums. */
+HELIO_API int helio_loss_bwd_packed(const float* img, const float* target, const float* dmaps, const float* tx,
+                          const float* g_per_img, const float* g_packed, const float* g_img_in,
+                          int B, int R, float* g_img, void* stream);
+
+/* packed[0..1] = sum_b per_img[b][0..1]: the numerators of F.mse_loss(pred_n, targ_n) and of
+ * (err * distance_maps).sum((1,2)).mean() (test_environment.py:456-457).  Ordered, deterministic. */
+HELIO_API int helio_loss_pack(const float* per_img, int B, float* packed, void* stream);
+
+/* One call for the whole forward of HelioEnv.step (test_environment.py:402-457): enqueues
+ *   K1 noisy field (+ ideal normals, boundary, alignment)   :414-421, :455, :460-470
+ *   K2 img
+ *   [render_target != 0]  K1 + K2 of the error-free field aimed with the ideal normals -> target,
+ *                         tx = max(target).clamp_min(1e-6)                                :429-436
+ *   K4 per_img, packed[4] = { sum diff^2, sum |diff| dmaps, sum bounds, sum angles }      :438-457
+ * The caller divides packed by {B R^2, B, B N, B N} (after an all-reduce when B is sharded).
+ * render_target == 0 reuses the caller's target / tx (they depend on sun only).
+ * tgt_params[B][N][4], tgt_actual/tgt_refl[B][N][3] are scratch for the target render (may be NULL
+ * when render_target == 0).  `workspace` as for helio_geom_fwd.  Same launches, same results as
+ * calling the individual entry points; it exists to cut host overhead for small fields. */
+HELIO_API int helio_step_fwd(const helio_scene_t* scene_host, const float* helio, const float* sun,
+                   const float* action, const float* errs, const float* dmaps,
+                   int B, int N, int R, int impl, int render_target,
+                   float* params, float* actual, float* refl, float* ideal, float* bounds, float* angles,
+                   float* img, float* target, float* tx, float* per_img, float* packed,
+                   float* tgt_params, float* tgt_actual, float* tgt_refl,
+                   void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Backward of helio_step_fwd down to g_action[B][N][3]: K4' (g_img) -> K3 (moments) -> K1'.
+ * g_packed[4] (device) = upstream grads of packed; g_per_img[B][3], g_img_in[B][R][R] (gradient
+ * arriving through obs['img']), g_actual, g_refl [B][N][3], g_bounds, g_angles [B][N] may be NULL.
+ * g_img[B][R][R] and moments[B][N][4] are scratch. */
+HELIO_API int helio_step_bwd(const helio_scene_t* scene_host, const float* helio, const float* sun,
+                   const float* action, const float* errs, const float* params,
+                   const float* img, const float* target, const float* dmaps, const float* tx,
+                   int B, int N, int R, int impl,
+                   const float* g_packed, const float* g_per_img, const float* g_img_in,
+                   const float* g_actual, const float* g_refl, const float* g_bounds, const float* g_angles,
+                   float* g_img, float* moments, float* g_action, void* stream);
 
 #ifdef __cplusplus
 }

@@ -18,7 +18,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.helio_abi_version() == 1
+    assert lib.helio_abi_version() == _lib.ABI_VERSION
     assert int(re.search(r"#define HELIO_ABI_VERSION (\d+)", header).group(1)) == _lib.ABI_VERSION
 
 

@@ -87,9 +87,12 @@ def _env_from_golden(g, **kw):
 
 @pytest.mark.parametrize("name", ENV)
 @pytest.mark.parametrize("cache", [False, True])
-def test_env_step_matches_reference(name, cache):
+@pytest.mark.parametrize("fused", [True, False], ids=["fused", "composed"])
+def test_env_step_matches_reference(name, cache, fused):
     g = load_golden("env_" + name)
-    env = _env_from_golden(g, cache_target=cache)
+    if not fused and name in ("mask", "exprisk"):
+        pytest.skip("these variants always take the composed path")
+    env = _env_from_golden(g, cache_target=cache, fused_step=fused)
     B, R = int(g["B"]), int(g["R"])
     # set_sun_pos products (test_environment.py:359-370): target render -> threshold at 0.5*max -> scipy EDT.
     # A pixel within 1e-4 of the threshold may flip between two fp32 renders and moves distances by <= 1 pixel.
@@ -120,6 +123,62 @@ def test_env_step_matches_reference(name, cache):
         for k in ("mse", "dist", "bound", "alignment_loss"):
             gr, = torch.autograd.grad(metrics[k], action, retain_graph=True, allow_unused=True)
             assert rel_err(gr.cpu().numpy(), g["grad_" + k]) < GRAD_TOL, k
+
+
+def test_fused_step_equals_composed_step():
+    """helio_step_fwd / helio_step_bwd enqueue the same kernels as the composed autograd graph: every output and
+    every gradient path (metrics, obs['img'], monitor tensors) must agree to summation-order rounding."""
+    g = load_golden("env_trainer")
+    outs = []
+    for fused in (True, False):
+        env = _env_from_golden(g, fused_step=fused)
+        env.distance_maps = _t(g["distance_maps"])
+        action = _t(g["action"]).requires_grad_(True)
+        obs, m, mon = env.step(action)
+        torch.manual_seed(3)
+        w_img = torch.randn_like(obs["img"])
+        w_refl = torch.randn_like(mon["reflected_rays"])
+        w_b = torch.randn_like(mon["all_bounds"])
+        w_mae = torch.randn_like(mon["mae_image"])
+        grads = {}
+        grads["metrics"], = torch.autograd.grad(m["mse"] + 0.01 * m["dist"] + m["bound"] + m["alignment_loss"], action, retain_graph=True)
+        grads["img"], = torch.autograd.grad((obs["img"] * w_img).sum(), action, retain_graph=True)
+        grads["monitor"], = torch.autograd.grad((mon["reflected_rays"] * w_refl).sum() + (mon["all_bounds"] * w_b).sum()
+                                                + (mon["mae_image"] * w_mae).sum(), action, retain_graph=True)
+        grads["all"], = torch.autograd.grad(m["mse"] + (obs["img"] * w_img).sum() + (mon["mae_image"] * w_mae).sum(), action)
+        outs.append((obs, m, mon, grads))
+    (o1, m1, mon1, g1), (o2, m2, mon2, g2) = outs
+    assert torch.equal(o1["img"], o2["img"]) and torch.equal(o1["aux"], o2["aux"])
+    for k in m1:
+        np.testing.assert_allclose(float(m1[k]), float(m2[k]), rtol=2e-6, err_msg=k)
+    for k in mon1:
+        assert torch.equal(mon1[k], mon2[k]), k
+    for k in g1:
+        assert rel_err(g1[k].cpu().numpy(), g2[k].cpu().numpy()) < 2e-6, k
+
+
+def test_graphed_step_replays_eager_step():
+    """CUDA-graph capture of step + backward: replays must reproduce the eager results bit for
+    bit at new actions, which also proves that no entry point allocates or synchronises."""
+    from doodle_b200 import GraphedStep
+    g = load_golden("env_trainer")
+    env = _env_from_golden(g)
+    env.distance_maps = _t(g["distance_maps"])
+    env.reset()
+    gs = GraphedStep(env, objective=lambda m: m["mse"] + 0.01 * m["dist"] + m["bound"] + m["alignment_loss"])
+    assert gs.helio_kernels_per_replay == 10          # 7 forward + 3 backward kernels
+    torch.manual_seed(11)
+    for rep in range(3):
+        action = torch.nn.functional.normalize(_t(g["action"]).view(int(g["B"]), -1, 3) + 0.02 * rep * torch.randn(int(g["B"]), env.num_heliostats, 3, device=_dev()), dim=2)
+        loss, grad = gs(action)
+        a = action.clone().requires_grad_(True)
+        obs, m, mon = env.step(a)
+        ref = m["mse"] + 0.01 * m["dist"] + m["bound"] + m["alignment_loss"]
+        gref, = torch.autograd.grad(ref, a)
+        assert torch.equal(gs.obs["img"], obs["img"])
+        assert torch.equal(loss, ref.detach()) and torch.equal(grad, gref)
+        for k in m:
+            assert torch.equal(gs.metrics[k].detach(), m[k].detach()), k
 
 
 def test_env_reset_matches_reference():
