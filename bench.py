@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--splat", default="auto", choices=["auto", "simt", "tc"])
     ap.add_argument("--cache-target", action="store_true", help="cache the target render (exact; off = reference-faithful)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-small-field", action="store_true", help="skip the N=50, R=128, B=25 env-steps/s side measurement")
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget for the cpu_baseline sample")
     return ap.parse_args()
 
@@ -258,6 +259,45 @@ def measure_tf32_peak(torch):
         torch.backends.cuda.matmul.allow_tf32 = prev
 
 
+def small_field_numbers(torch, dev, iters=300):
+    """BASELINE.json configs[1]: HelioEnv reset/step, N=50, 128x128, B=25, new errors every reset, all four losses +
+    backward.  Launch/host-latency bound, so reported as env-steps/s: the default eager path (one device sync per step
+    for the reference's NaN/Inf asserts) and the CUDA-graph replay of the same step (doodle_b200.GraphedStep)."""
+    from doodle_b200 import GraphedStep, HelioEnv
+    N, R, B = 50, 128, 25
+    helio, targ_pos, targ_norm, area, _ = make_inputs(N, B)
+    torch.manual_seed(7)
+    env = HelioEnv(heliostat_pos=helio.to(dev), targ_pos=targ_pos.to(dev), targ_area=area, targ_norm=targ_norm.to(dev), sigma_scale=0.1,
+                   error_scale_mrad=90.0, resolution=R, batch_size=B, device=str(dev), new_errors_every_reset=True)
+    env.reset()
+    a0 = env.ideal_normals.flatten(1).clone()
+
+    def eager():
+        a = a0.detach().requires_grad_(True)
+        obs, m, mon = env.step(a)
+        (m["mse"] + m["dist"] + m["bound"] + m["alignment_loss"]).backward()
+
+    def clock(fn, n):
+        for _ in range(10):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    ms_eager = clock(eager, iters)
+    gs = GraphedStep(env)
+    ms_graph = clock(lambda: gs(a0), iters)
+    return dict(workload="HelioEnv.step + backward, N=50 R=128 B=25 (BASELINE.json configs[1])", env_steps_per_s=1e3 / ms_eager,
+                us_per_step=ms_eager * 1e3, env_steps_per_s_graphed=1e3 / ms_graph, us_per_step_graphed=ms_graph * 1e3,
+                evals_per_s=B * N * R * R / (ms_eager * 1e-3), helio_kernels_per_step=gs.helio_kernels_per_replay,
+                note="eager = public API incl. the per-step finite check (1 sync); graphed = CUDA-graph replay of the same step")
+
+
 def main_ours(args):
     import torch
     import torch.distributed as dist
@@ -394,6 +434,12 @@ def main_ours(args):
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:      # reported at N=1 only
         cpu_baseline, _ = run_cpu_sample(N, R, budget_s=args.cpu_seconds)
+    small = None
+    if world == 1 and not args.no_small_field:
+        try:
+            small = small_field_numbers(torch, dev)
+        except Exception as e:  # the headline line must still print
+            small = dict(error=repr(e))
 
     line = dict(metric=METRIC, value=evals_step / (ms_step * 1e-3), unit=UNIT, n_gpus=world, steps=steps, warmup=warmup,
                 ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
@@ -404,7 +450,7 @@ def main_ours(args):
                 clocks=clocks,
                 e2e=dict(value=evals_step / (ms_e2e * 1e-3), unit=UNIT, ms_per_step=ms_e2e,
                          h2d_bytes_per_step=h_action.numel() * 4, d2h_bytes_per_step=h_grad.numel() * 4 + 16),
-                gpu_launches=launches, roofline=roofline, cpu_baseline=cpu_baseline)
+                gpu_launches=launches, roofline=roofline, cpu_baseline=cpu_baseline, small_field=small)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -2,6 +2,7 @@
 #include <atomic>
 #include <cstdlib>
 #include <mutex>
+#include <vector>
 
 #include "geom.cuh"
 #include "loss.cuh"
@@ -60,6 +61,33 @@ std::atomic<int>& tc_pair_state() {
 }
 int tc_pair_mode() { return tc_pair_state().load(std::memory_order_relaxed); }
 
+// ---- opt-in per-kernel timing (helio_profile_*): CUDA events recorded around every kernel this library
+// enqueues, on the stream it is enqueued on.  Off by default; not for use under stream capture.
+struct ProfRecord {
+    const char* name;
+    cudaEvent_t e0, e1;
+};
+std::atomic<int> g_prof_on{0};
+std::mutex g_prof_mu;
+std::vector<ProfRecord> g_prof;
+
+struct KernelTimer {
+    cudaStream_t st;
+    ProfRecord rec{nullptr, nullptr, nullptr};
+    KernelTimer(const char* name, void* stream) : st((cudaStream_t)stream) {
+        if (!g_prof_on.load(std::memory_order_relaxed)) return;
+        if (cudaEventCreate(&rec.e0) != cudaSuccess || cudaEventCreate(&rec.e1) != cudaSuccess) return;
+        rec.name = name;
+        cudaEventRecord(rec.e0, st);
+    }
+    ~KernelTimer() {
+        if (!rec.name) return;
+        cudaEventRecord(rec.e1, st);
+        std::lock_guard<std::mutex> lk(g_prof_mu);
+        g_prof.push_back(rec);
+    }
+};
+
 inline unsigned geom_blocks(int B, int N) { return (unsigned)(((long long)B * N + kGeomThreads - 1) / kGeomThreads); }
 
 }  // namespace
@@ -81,6 +109,32 @@ HELIO_API int helio_set_tc_pair_mode(int mode) {
     return 0;
 }
 
+HELIO_API int helio_profile_enable(int on) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    for (auto& r : g_prof) {
+        cudaEventDestroy(r.e0);
+        cudaEventDestroy(r.e1);
+    }
+    g_prof.clear();
+    g_prof_on.store(on ? 1 : 0, std::memory_order_relaxed);
+    return 0;
+}
+
+HELIO_API int helio_profile_count(void) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    return (int)g_prof.size();
+}
+
+HELIO_API int helio_profile_get(int index, const char** name, float* ms) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    HELIO_REQUIRE(index >= 0 && index < (int)g_prof.size() && name && ms, "profile record index");
+    const ProfRecord& r = g_prof[index];
+    HELIO_CUDA_OK(cudaEventSynchronize(r.e1));
+    HELIO_CUDA_OK(cudaEventElapsedTime(ms, r.e0, r.e1));
+    *name = r.name;
+    return 0;
+}
+
 HELIO_API int64_t helio_geom_workspace_bytes(int B, int N) {
     if (B <= 0 || N <= 0) return 0;
     return (int64_t)sizeof(GeomWorkspace) + (int64_t)geom_blocks(B, N) * 2 * sizeof(float);
@@ -98,6 +152,7 @@ HELIO_API int helio_geom_fwd(const helio_scene_t* scene, const float* helio_pos,
         if (workspace_bytes < helio_geom_workspace_bytes(B, N))
             return set_error(HELIO_E_WORKSPACE, "geom workspace too small%s%s");
     }
+    KernelTimer timer("geom_fwd", stream);
     geom_fwd_kernel<<<geom_blocks(B, N), kGeomThreads, 0, (cudaStream_t)stream>>>(
         make_scene(scene), helio_pos, sun, action, errs, B, N, reinterpret_cast<float4*>(params), actual, refl, ideal,
         bounds, angles, sums, reinterpret_cast<GeomWorkspace*>(workspace));
@@ -112,6 +167,7 @@ HELIO_API int helio_geom_bwd(const helio_scene_t* scene, const float* helio_pos,
     if (int rc = require_device(&d)) return rc;
     HELIO_REQUIRE(scene && helio_pos && sun && action && g_action, "null pointer");
     HELIO_REQUIRE(B > 0 && N > 0, "B, N must be positive");
+    KernelTimer timer("geom_bwd", stream);
     geom_bwd_kernel<<<geom_blocks(B, N), kGeomThreads, 0, (cudaStream_t)stream>>>(
         make_scene(scene), helio_pos, sun, action, errs, B, N, reinterpret_cast<const float4*>(g_moments), g_actual,
         g_refl, g_bounds, g_angles, g_sums, g_action);
@@ -126,6 +182,7 @@ HELIO_API int helio_splat_fwd(const float* params, int B, int N, int R, float wi
     HELIO_REQUIRE(params && img, "null pointer");
     HELIO_REQUIRE(B > 0 && N > 0 && R > 0, "B, N, R must be positive");
     HELIO_REQUIRE(impl >= HELIO_SPLAT_AUTO && impl <= HELIO_SPLAT_TC, "unknown impl");
+    KernelTimer timer("splat_fwd", stream);
     const bool tc_ok = splat_tc_fwd_supported(B, N, R);
     if (impl == HELIO_SPLAT_TC && !tc_ok)
         return set_error(HELIO_E_BADARG, "tcgen05 splat forward does not support this shape%s%s");
@@ -144,6 +201,7 @@ HELIO_API int helio_splat_bwd(const float* params, const float* g_img, int B, in
     HELIO_REQUIRE(params && g_img && moments, "null pointer");
     HELIO_REQUIRE(B > 0 && N > 0 && R > 0, "B, N, R must be positive");
     HELIO_REQUIRE(impl >= HELIO_SPLAT_AUTO && impl <= HELIO_SPLAT_TC, "unknown impl");
+    KernelTimer timer("splat_bwd", stream);
     const bool tc_ok = splat_tc_bwd_supported(B, N, R);
     if (impl == HELIO_SPLAT_TC && !tc_ok)
         return set_error(HELIO_E_BADARG, "tcgen05 splat backward does not support this shape%s%s");
@@ -161,6 +219,7 @@ HELIO_API int helio_image_max(const float* target, int B, int R, float* tx, void
     HELIO_REQUIRE(target && tx, "null pointer");
     HELIO_REQUIRE(B > 0 && R > 0, "B, R must be positive");
     const int slices = loss_slices(B, R, d->sms);
+    KernelTimer timer("image_max", stream);
     HELIO_CUDA_OK(launch_image_clusters(image_max_kernel, B, slices, (cudaStream_t)stream, target, R, slices, tx));
     return 0;
 }
@@ -172,6 +231,7 @@ HELIO_API int helio_loss_fwd(const float* img, const float* target, const float*
     HELIO_REQUIRE(img && target && dmaps && tx && per_img, "null pointer");
     HELIO_REQUIRE(B > 0 && R > 0, "B, R must be positive");
     const int slices = loss_slices(B, R, d->sms);
+    KernelTimer timer("loss_fwd", stream);
     HELIO_CUDA_OK(launch_image_clusters(loss_fwd_kernel, B, slices, (cudaStream_t)stream, img, target, dmaps, tx, R, slices, per_img));
     return 0;
 }
@@ -195,6 +255,7 @@ HELIO_API int helio_loss_bwd_packed(const float* img, const float* target, const
     const int want = (2 * d->sms + B - 1) / B;
     if (slices > want) slices = want;
     if (slices < 1) slices = 1;
+    KernelTimer timer("loss_bwd", stream);
     loss_bwd_kernel<<<(unsigned)((long long)B * slices), kLossThreads, 0, (cudaStream_t)stream>>>(
         img, target, dmaps, tx, g_per_img, g_packed, g_img_in, R, slices, g_img);
     HELIO_CUDA_OK(cudaGetLastError());
@@ -206,6 +267,7 @@ HELIO_API int helio_loss_pack(const float* per_img, int B, float* packed, void* 
     if (int rc = require_device(&d)) return rc;
     HELIO_REQUIRE(per_img && packed, "null pointer");
     HELIO_REQUIRE(B > 0, "B must be positive");
+    KernelTimer timer("loss_pack", stream);
     loss_pack_kernel<<<1, kLossThreads, 0, (cudaStream_t)stream>>>(per_img, B, packed);
     HELIO_CUDA_OK(cudaGetLastError());
     return 0;

@@ -25,27 +25,28 @@ from ._lib import SPLAT_AUTO, SPLAT_SIMT, SPLAT_TC, Scene  # noqa: F401
 
 # ---- launch accounting / live per-kernel timing (bench.py reads these) ------------------------
 _LAUNCHES = 0
-_PROFILE = {"on": False, "events": []}
 
 
 def launch_count() -> int:
-    """Number of libhelio kernels launched by this process so far (one per C-ABI compute call)."""
+    """Number of libhelio kernels launched by this process so far."""
     return _LAUNCHES
 
 
 def reset_profile(enabled: bool):
-    _PROFILE["on"] = bool(enabled)
-    _PROFILE["events"] = []
+    """Switch the library's per-kernel CUDA-event timing on/off (helio_profile_enable); clears earlier records."""
+    _lib.check(_lib.load().helio_profile_enable(1 if enabled else 0), "helio_profile_enable")
 
 
 def collect_profile():
-    """{kernel: {n, total_ms, avg_ms}} from CUDA events recorded around each call on its stream."""
-    torch.cuda.synchronize()
+    """{kernel: {n, total_ms, avg_ms}} from the CUDA events the library recorded around each kernel on its stream."""
+    lib = _lib.load()
     out = {}
-    for name, e0, e1 in _PROFILE["events"]:
-        d = out.setdefault(name, dict(n=0, total_ms=0.0))
+    name, ms = C.c_char_p(), C.c_float()
+    for i in range(lib.helio_profile_count()):
+        _lib.check(lib.helio_profile_get(i, C.byref(name), C.byref(ms)), "helio_profile_get")
+        d = out.setdefault(name.value.decode(), dict(n=0, total_ms=0.0))
         d["n"] += 1
-        d["total_ms"] += e0.elapsed_time(e1)
+        d["total_ms"] += ms.value
     for d in out.values():
         d["avg_ms"] = d["total_ms"] / d["n"]
     return out
@@ -53,12 +54,11 @@ def collect_profile():
 
 class _Call:
     """Context manager around one C-ABI launch: device guard (only when the tensors live on another
-    device than the current one), launch count, optional CUDA events."""
+    device than the current one) and launch count."""
 
-    __slots__ = ("name", "guard", "e0")
+    __slots__ = ("guard",)
 
     def __init__(self, name: str, device: torch.device):
-        self.name = name
         self.guard = None if device.index is None or device.index == torch._C._cuda_getDevice() else torch.cuda.device(device)
 
     def __enter__(self):
@@ -66,16 +66,9 @@ class _Call:
         if self.guard is not None:
             self.guard.__enter__()
         _LAUNCHES += 1
-        if _PROFILE["on"]:
-            self.e0 = torch.cuda.Event(enable_timing=True)
-            self.e0.record()
         return self
 
     def __exit__(self, *exc):
-        if _PROFILE["on"]:
-            e1 = torch.cuda.Event(enable_timing=True)
-            e1.record()
-            _PROFILE["events"].append((self.name, self.e0, e1))
         if self.guard is not None:
             return self.guard.__exit__(*exc)
         return False

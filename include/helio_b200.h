@@ -71,6 +71,16 @@ HELIO_API int helio_device_ok(void);
  * No reference counterpart (tuning / A-B switch of this library). */
 HELIO_API int helio_set_tc_pair_mode(int mode);
 
+/* Opt-in per-kernel timing (no reference counterpart; SURVEY.md section 5 "tracing / profiling").
+ * helio_profile_enable(1) clears earlier records and makes every entry point record a CUDA event pair
+ * around each kernel it enqueues, on the caller's stream; helio_profile_enable(0) stops and clears.
+ * helio_profile_get waits for record `index` and returns the kernel's name (static string: geom_fwd,
+ * splat_fwd, image_max, loss_fwd, loss_pack, loss_bwd, splat_bwd, geom_bwd) and its duration in ms.
+ * Creating events allocates driver resources: keep it off in production and under stream capture. */
+HELIO_API int helio_profile_enable(int on);
+HELIO_API int helio_profile_count(void);
+HELIO_API int helio_profile_get(int index, const char** name, float* ms);
+
 /* Bytes of workspace helio_geom_fwd needs for (B, N) (block partials + ticket counter).  The
  * workspace must be zero-initialised ONCE by the caller; the kernel leaves it zeroed. */
 HELIO_API int64_t helio_geom_workspace_bytes(int B, int N);
