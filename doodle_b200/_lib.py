@@ -21,6 +21,7 @@ EXPORTS = (
     "helio_abi_version", "helio_last_error", "helio_device_ok", "helio_set_tc_pair_mode", "helio_geom_workspace_bytes", "helio_geom_fwd",
     "helio_geom_bwd", "helio_splat_fwd", "helio_splat_bwd", "helio_image_max", "helio_loss_fwd", "helio_loss_bwd",
     "helio_profile_enable", "helio_profile_count", "helio_profile_get",
+    "helio_distance_maps_workspace_bytes", "helio_distance_maps",
     "helio_loss_bwd_packed", "helio_loss_pack", "helio_step_fwd", "helio_step_bwd",
 )
 
@@ -70,6 +71,10 @@ def _declare(lib):
     lib.helio_profile_count.argtypes = []
     lib.helio_profile_get.restype = i
     lib.helio_profile_get.argtypes = [i, C.POINTER(C.c_char_p), C.POINTER(C.c_float)]
+    lib.helio_distance_maps_workspace_bytes.restype = i64
+    lib.helio_distance_maps_workspace_bytes.argtypes = [i, i]
+    lib.helio_distance_maps.restype = i
+    lib.helio_distance_maps.argtypes = [p, i, i, f, p, p, i64, p]
     lib.helio_geom_workspace_bytes.restype = i64
     lib.helio_geom_workspace_bytes.argtypes = [i, i]
     lib.helio_geom_fwd.restype = i

@@ -4,6 +4,7 @@
 #include <mutex>
 #include <vector>
 
+#include "edt.cuh"
 #include "geom.cuh"
 #include "loss.cuh"
 #include "splat_simt.cuh"
@@ -220,7 +221,43 @@ HELIO_API int helio_image_max(const float* target, int B, int R, float* tx, void
     HELIO_REQUIRE(B > 0 && R > 0, "B, R must be positive");
     const int slices = loss_slices(B, R, d->sms);
     KernelTimer timer("image_max", stream);
-    HELIO_CUDA_OK(launch_image_clusters(image_max_kernel, B, slices, (cudaStream_t)stream, target, R, slices, tx));
+    HELIO_CUDA_OK(launch_image_clusters(image_max_kernel, B, slices, (cudaStream_t)stream, target, R, slices, 1e-6f, tx));
+    return 0;
+}
+
+HELIO_API int64_t helio_distance_maps_workspace_bytes(int B, int R) {
+    if (B <= 0 || R <= 0) return 0;
+    return (((int64_t)B * 4 + 255) / 256) * 256 + (int64_t)B * R * R * 2;
+}
+
+HELIO_API int helio_distance_maps(const float* img, int B, int R, float thr, float* dmaps, void* workspace,
+                        int64_t workspace_bytes, void* stream) {
+    const DeviceInfo* d = nullptr;
+    if (int rc = require_device(&d)) return rc;
+    HELIO_REQUIRE(img && dmaps && workspace, "null pointer");
+    HELIO_REQUIRE(B > 0 && R > 0 && R <= kEdtMaxR, "B, R must be positive (R <= 4096)");
+    if (workspace_bytes < helio_distance_maps_workspace_bytes(B, R)) return set_error(HELIO_E_WORKSPACE, "edt workspace too small%s%s");
+    float* mx = reinterpret_cast<float*>(workspace);
+    short* g = reinterpret_cast<short*>(reinterpret_cast<char*>(workspace) + (((int64_t)B * 4 + 255) / 256) * 256);
+    cudaStream_t st = (cudaStream_t)stream;
+    {
+        KernelTimer timer("edt_max", stream);
+        const int slices = loss_slices(B, R, d->sms);
+        HELIO_CUDA_OK(launch_image_clusters(image_max_kernel, B, slices, st, img, R, slices, -INFINITY, mx));
+    }
+    {
+        KernelTimer timer("edt_cols", stream);
+        edt_cols_kernel<<<(unsigned)(((long long)B * R + kEdtThreads - 1) / kEdtThreads), kEdtThreads, 0, st>>>(img, mx, thr, B, R, g);
+        HELIO_CUDA_OK(cudaGetLastError());
+    }
+    {
+        KernelTimer timer("edt_rows", stream);
+        constexpr int warps = kEdtThreads / 32;
+        const size_t smem = (size_t)warps * R * sizeof(int);
+        HELIO_CUDA_OK(cudaFuncSetAttribute(edt_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        edt_rows_kernel<<<(unsigned)(((long long)B * R + warps - 1) / warps), kEdtThreads, smem, st>>>(g, B, R, dmaps);
+        HELIO_CUDA_OK(cudaGetLastError());
+    }
     return 0;
 }
 

@@ -45,9 +45,9 @@ __device__ __forceinline__ float ld_dsmem(const float* local, uint32_t rank) {
     return v;
 }
 
-// tx[b] = max(max target[b], 1e-6).
+// tx[b] = max(max target[b], floor)   (floor = 1e-6 for the loss normaliser, -inf for the raw maximum).
 __global__ void __launch_bounds__(kLossThreads)
-image_max_kernel(const float* __restrict__ target, int R, int slices, float* __restrict__ tx) {
+image_max_kernel(const float* __restrict__ target, int R, int slices, float floor, float* __restrict__ tx) {
     const int b = blockIdx.x / slices, s = blockIdx.x % slices;
     const size_t npix = (size_t)R * R, stride = (size_t)slices * kLossThreads;
     const float* t = target + (size_t)b * npix;
@@ -76,11 +76,11 @@ image_max_kernel(const float* __restrict__ target, int R, int slices, float* __r
         if (s == 0 && threadIdx.x == 0) {
             float x = part;
             for (int r = 1; r < slices; ++r) x = fmaxf(x, ld_dsmem(&part, (uint32_t)r));
-            tx[b] = fmaxf(x, 1e-6f);
+            tx[b] = fmaxf(x, floor);
         }
         cluster_barrier();   // peers keep their shared memory alive until the leader has read it
     } else if (threadIdx.x == 0) {
-        tx[b] = fmaxf(part, 1e-6f);
+        tx[b] = fmaxf(part, floor);
     }
 }
 

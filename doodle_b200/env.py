@@ -29,6 +29,7 @@ from scipy.ndimage import distance_transform_edt
 
 from .field import HelioField
 from .functional import ImageLossFn, StepFn, _cf, image_max, require_cuda
+from .functional import distance_maps as _distance_maps_cuda
 
 try:  # gymnasium is optional: only Env / spaces.Box / spaces.Dict are touched (test_environment.py:11-12)
     import gymnasium as gym
@@ -90,9 +91,16 @@ def sample_cone_directions(n: int, axis: torch.Tensor, half_angle_deg: float, de
     return dirs
 
 
-def make_distance_maps(imgs: torch.Tensor, thr: float = 0.5) -> torch.Tensor:
-    """Per-image Euclidean distance to the >thr*max region (test_environment.py:92-97; scipy EDT on
-    the host, setup time only)."""
+def make_distance_maps(imgs: torch.Tensor, thr: float = 0.5, impl: str = "auto") -> torch.Tensor:
+    """Per-image Euclidean distance to the >thr*max region (test_environment.py:92-97).
+
+    CUDA tensors go through the exact GPU transform (helio_distance_maps, bit-identical to scipy's exact EDT:
+    no device->host->device round trip, no Python loop over B); ``impl="scipy"`` keeps the reference's host path
+    (the only one available for CPU tensors, which the product never produces)."""
+    if impl not in ("auto", "cuda", "scipy"):
+        raise ValueError(f"unknown distance-map implementation {impl!r}")
+    if impl == "cuda" or (impl == "auto" and imgs.is_cuda):
+        return _distance_maps_cuda(imgs, thr)
     maps = []
     for img in imgs.detach().cpu().numpy():
         mask = (img > thr * img.max()).astype(np.uint8)
@@ -126,6 +134,7 @@ class HelioEnv(_EnvBase):
                  cache_target=False,
                  check_finite=True,
                  fused_step=True,
+                 distance_maps_impl="auto",
                  ):
         super().__init__()
         require_cuda(torch.device(device), "HelioEnv")
@@ -159,6 +168,7 @@ class HelioEnv(_EnvBase):
         self.cache_target = cache_target
         self.check_finite = check_finite
         self.fused_step = fused_step
+        self.distance_maps_impl = distance_maps_impl   # "auto"/"cuda": GPU EDT; "scipy": the reference's host path
         self._target_cache = None
 
         action_dim = heliostat_pos.shape[0] * 3
@@ -222,7 +232,7 @@ class HelioEnv(_EnvBase):
         with torch.no_grad():
             ideal_normals = self.ref_field.calculate_ideal_normals(self.sun_pos)
             timg, _ = self.ref_field.render(self.sun_pos, self.ref_field.initial_action, ideal_normals)
-        self.distance_maps = make_distance_maps(timg)
+        self.distance_maps = make_distance_maps(timg, impl=self.distance_maps_impl)
         self.ref_min = torch.min(timg)
         self.ref_max = torch.max(timg)
 

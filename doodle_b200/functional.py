@@ -184,6 +184,24 @@ def image_max(target: torch.Tensor) -> torch.Tensor:
     return tx
 
 
+def distance_maps(imgs: torch.Tensor, thr: float = 0.5) -> torch.Tensor:
+    """Exact EDT of ``imgs > thr * max`` per image on the GPU (helio_distance_maps); replaces the host round trip
+    through scipy.ndimage.distance_transform_edt of make_distance_maps (test_environment.py:92-97), bit for bit."""
+    lib = _lib.load()
+    imgs = _cf(imgs.detach())
+    B, R = imgs.shape[0], imgs.shape[-1]
+    assert imgs.dim() == 3 and imgs.shape[1] == R, "distance_maps expects [B, R, R]"
+    out = torch.empty_like(imgs)
+    nbytes = lib.helio_distance_maps_workspace_bytes(B, R)
+    ws = torch.empty((nbytes + 3) // 4, dtype=torch.int32, device=imgs.device)
+    with _Call("distance_maps", imgs.device):
+        rc = lib.helio_distance_maps(_ptr(imgs), B, R, float(thr), _ptr(out), _ptr(ws), nbytes, _stream())
+    _lib.check(rc, "helio_distance_maps")
+    global _LAUNCHES
+    _LAUNCHES += 2
+    return out
+
+
 class ImageLossFn(torch.autograd.Function):
     """K4: img -> per_img[B,3] = {sum diff^2, sum |diff| dmaps, sum |diff|}, diff=(img-target)/tx."""
 

@@ -135,6 +135,15 @@ HELIO_API int helio_splat_bwd(const float* params, const float* g_img, int B, in
 /* tx[b] = max(max_ij target[b], 1e-6)   (test_environment.py:436). */
 HELIO_API int helio_image_max(const float* target, int B, int R, float* tx, void* stream);
 
+/* Distance maps of set_sun_pos: replaces make_distance_maps (test_environment.py:92-97), i.e. per image
+ *   mask = img > thr * img.max();  dmap = float32(scipy.ndimage.distance_transform_edt(1 - mask))
+ * with an exact integer separable transform on the GPU (bit-identical to scipy's exact EDT; an image
+ * without mask pixels reproduces scipy's result for an input without background).
+ * img, dmaps [B][R][R]; workspace: helio_distance_maps_workspace_bytes(B, R) bytes, no initialisation. */
+HELIO_API int64_t helio_distance_maps_workspace_bytes(int B, int R);
+HELIO_API int helio_distance_maps(const float* img, int B, int R, float thr, float* dmaps,
+                        void* workspace, int64_t workspace_bytes, void* stream);
+
 /* K4 forward: per-image loss partials of HelioEnv.step (test_environment.py:438-457,492):
  *   diff = (img - target)/tx ;  per_img[b] = { sum diff^2, sum |diff| dmaps, sum |diff| }.
  * The caller forms mse = sum_b per_img[b][0]/(B R^2), dist = mean_b per_img[b][1],

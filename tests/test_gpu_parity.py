@@ -181,6 +181,43 @@ def test_graphed_step_replays_eager_step():
             assert torch.equal(gs.metrics[k].detach(), m[k].detach()), k
 
 
+@pytest.mark.parametrize("B,R", [(3, 16), (5, 33), (4, 128), (2, 200), (2, 512), (40, 64)])
+def test_gpu_distance_maps_bit_exact_vs_scipy(B, R):
+    """helio_distance_maps vs make_distance_maps' scipy path (test_environment.py:92-97): exact EDT, so bit-equal."""
+    from doodle_b200 import make_distance_maps
+    torch.manual_seed(B * 1000 + R)
+    xs = torch.linspace(-1, 1, R, device=_dev())
+    imgs = []
+    for b in range(B):
+        if b % 4 == 3:          # sparse random features, many empty columns
+            img = (torch.rand(R, R, device=_dev()) > 0.995).float() * (1 + torch.rand(R, R, device=_dev()))
+        else:                   # a few Gaussian blobs, as the renderer produces
+            img = torch.zeros(R, R, device=_dev())
+            for _ in range(1 + b % 3):
+                cx, cy, s = (torch.rand(3) * torch.tensor([1.6, 1.6, 0.3]) - torch.tensor([0.8, 0.8, -0.02])).tolist()
+                img = img + torch.exp(-((xs[:, None] - cx) ** 2 + (xs[None, :] - cy) ** 2) / (2 * s * s))
+        imgs.append(img)
+    imgs = torch.stack(imgs)
+    got = make_distance_maps(imgs, impl="cuda")
+    ref = make_distance_maps(imgs, impl="scipy")
+    assert got.dtype == torch.float32 and got.shape == ref.shape
+    assert torch.equal(got, ref), float((got - ref).abs().max())
+
+
+def test_gpu_distance_maps_edge_cases():
+    from doodle_b200 import make_distance_maps
+    R = 24
+    imgs = torch.zeros(4, R, R, device=_dev())
+    imgs[1] = 1.0                      # constant image: nothing exceeds 0.5*max?  1 > 0.5 everywhere -> all mask
+    imgs[2, 5, 7] = 3.0                # single feature pixel
+    imgs[3, 0, 0] = 1.0
+    imgs[3, R - 1, R - 1] = 0.9        # two corners
+    for thr in (0.5, 0.3, 0.95):
+        got = make_distance_maps(imgs, thr=thr, impl="cuda")
+        ref = make_distance_maps(imgs, thr=thr, impl="scipy")   # imgs[0] has no mask pixel: scipy's virtual-pixel result
+        assert torch.equal(got, ref), (thr, float((got - ref).abs().max()))
+
+
 def test_env_reset_matches_reference():
     g = load_golden("env_readme")
     env = _env_from_golden(g)
