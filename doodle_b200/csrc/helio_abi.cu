@@ -289,7 +289,7 @@ HELIO_API int helio_loss_bwd_packed(const float* img, const float* target, const
     // enough CTAs to fill the machine even for small B
     const size_t vecs = ((size_t)R * R + 3) / 4;
     int slices = (int)((vecs + 4 * kLossThreads - 1) / (4 * kLossThreads));
-    const int want = (2 * d->sms + B - 1) / B;
+    const int want = (16 * d->sms + B - 1) / B;
     if (slices > want) slices = want;
     if (slices < 1) slices = 1;
     KernelTimer timer("loss_bwd", stream);

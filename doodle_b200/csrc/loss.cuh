@@ -138,7 +138,7 @@ loss_fwd_kernel(const float* __restrict__ img, const float* __restrict__ target,
 inline int loss_slices(int B, int R, int num_sms) {
     const size_t vecs = ((size_t)R * R + 3) / 4;
     int s = 1;
-    while (s < 8 && (long long)B * s < 2LL * num_sms && vecs / (size_t)(2 * s) >= (size_t)kLossThreads) s *= 2;
+    while (s < 8 && (long long)B * s < 8LL * num_sms && vecs / (size_t)(2 * s) >= (size_t)kLossThreads) s *= 2;
     return s;
 }
 

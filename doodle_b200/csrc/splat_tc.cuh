@@ -242,6 +242,9 @@ splat_fwd_tc_kernel(const float4* __restrict__ params, float* __restrict__ img, 
         for (int tile = group; tile < num_tiles; tile += ngroups) {
             const int b = tile / tiles_per_img, t = tile % tiles_per_img;
             const int g0 = (isA ? (t / tiles_j) * kTileM + (int)cx.rank * C::kM : (t % tiles_j) * NT + (int)cx.rank * C::kBRows) + wrow;
+            // operand rows beyond the image only feed accumulator rows / columns that are never stored: skip the
+            // Gaussians and leave the stage bytes as they are (accumulator rows and columns are independent)
+            const bool dead = g0 >= R;
             const uint32_t tab = (isA ? cx.sX_u : cx.sY_u) + (uint32_t)(g0 + rs) * 4u;
             float xr[8];
 #pragma unroll
@@ -270,6 +273,7 @@ splat_fwd_tc_kernel(const float4* __restrict__ params, float* __restrict__ img, 
                 const int s = it % C::kStages;
                 cx.producer_acquire(s, (it / C::kStages) & 1);
                 const uint32_t base = cx.smem_u + (uint32_t)(s * C::kStageBytes) + region;
+                if (!dead)
 #pragma unroll
                 for (int st = 0; st < 8; ++st) {
                     float hi[4], lo[4];
@@ -341,8 +345,9 @@ splat_fwd_tc_kernel(const float4* __restrict__ params, float* __restrict__ img, 
 
 inline bool splat_tc_fwd_supported(int B, int N, int R) { return B > 0 && N > 0 && R >= 8 && R <= kTcMaxR; }
 inline bool splat_tc_fwd_preferred(int B, int N, int R) {
-    // tensor path pays off once the contraction dimension and the image are large enough
-    return R >= 128 && N >= 64;
+    // measured on B200 over N in {50..5000}, R in {64..512}, B in {25..16384}: the tensor path wins (or ties within a
+    // few microseconds) everywhere, including N = 50; only very small images leave most of a 128-row tile dead
+    return R >= 48;
 }
 
 // launch `kernel` as a persistent grid of CTA groups (clusters of CG CTAs)
@@ -387,7 +392,8 @@ inline cudaError_t splat_tc_fwd(const float* params, float* img, int B, int N, i
         if (pair != 1 && num_sms >= 2) return launch_splat_fwd_tc<256, 2>(params, img, B, N, R, width, height, num_sms, st);
         return launch_splat_fwd_tc<256, 1>(params, img, B, N, R, width, height, num_sms, st);
     }
-    return launch_splat_fwd_tc<128, 1>(params, img, B, N, R, width, height, num_sms, st);
+    if (R > 64) return launch_splat_fwd_tc<128, 1>(params, img, B, N, R, width, height, num_sms, st);
+    return launch_splat_fwd_tc<64, 1>(params, img, B, N, R, width, height, num_sms, st);
 }
 
 // ================================================================================================
@@ -427,11 +433,19 @@ splat_bwd_tc_kernel(const float4* __restrict__ params, const float* __restrict__
         const int r = (warp % (C::kM / 32)) * 32 + lane;
         const int q0 = (warp / (C::kM / 32)) * kQ;
         uint32_t it = 0;
-        for (int tile = group; tile < num_tiles; tile += ngroups) {
+        // this row's footprint for a tile; the next tile's is fetched while the current one is generated
+        auto tile_params = [&](int tile, bool& live) {
             const int b = tile / nblocks, nb = tile % nblocks;
             const int n = nb * kTileH + (int)cx.rank * C::kM + r;
-            const bool live = n < N;
-            const float4 p = live ? __ldg(params + (size_t)b * N + n) : make_float4(0.f, 0.f, 0.f, 1.f);
+            live = tile < num_tiles && n < N;
+            return live ? __ldg(params + (size_t)b * N + n) : make_float4(0.f, 0.f, 0.f, 1.f);
+        };
+        bool live_next;
+        float4 p_next = tile_params(group, live_next);
+        for (int tile = group; tile < num_tiles; tile += ngroups) {
+            const bool live = live_next;
+            const float4 p = p_next;
+            p_next = tile_params(tile + ngroups, live_next);
             const float nk2 = -p.z;
             const float dead = live ? 0.f : -INFINITY;   // rows beyond N: 2^-inf = 0
 #pragma unroll 1
@@ -587,11 +601,20 @@ splat_bwd_tc_kernel(const float4* __restrict__ params, const float* __restrict__
         // ================= epilogue: accumulator -> moments =================
         const int q = warp & 3;
         uint32_t sub = 0;
+        auto tile_params = [&](int tile, bool& live) {
+            const int b = tile / nblocks, nb = tile % nblocks;
+            const int n = nb * kTileH + (int)cx.rank * C::kM + q * 32 + lane;
+            live = tile < num_tiles && n < N;
+            return live ? __ldg(params + (size_t)b * N + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+        };
+        bool live_next;
+        float4 p_next = tile_params(group, live_next);
         for (int tile = group; tile < num_tiles; tile += ngroups) {
             const int b = tile / nblocks, nb = tile % nblocks;
             const int n = nb * kTileH + (int)cx.rank * C::kM + q * 32 + lane;
-            const bool live = n < N;
-            const float4 p = live ? __ldg(params + (size_t)b * N + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const bool live = live_next;
+            const float4 p = p_next;
+            p_next = tile_params(tile + ngroups, live_next);
             const float nk2 = -p.z;
             float S0 = 0.f, Sx = 0.f, Sy = 0.f, S2 = 0.f;
 #pragma unroll 1
@@ -642,7 +665,7 @@ splat_bwd_tc_kernel(const float4* __restrict__ params, const float* __restrict__
 }
 
 inline bool splat_tc_bwd_supported(int B, int N, int R) { return B > 0 && N > 0 && R >= 8 && R <= kTcMaxR; }
-inline bool splat_tc_bwd_preferred(int B, int N, int R) { return R >= 128 && N >= 64; }
+inline bool splat_tc_bwd_preferred(int B, int N, int R) { return R >= 48; }
 
 template <int NT, int CG>
 inline cudaError_t launch_splat_bwd_tc(const float* params, const float* g_img, float* moments, int B, int N, int R,
