@@ -188,7 +188,11 @@ HELIO_API int helio_splat_fwd(const float* params, int B, int N, int R, float wi
     if (impl == HELIO_SPLAT_TC && !tc_ok)
         return set_error(HELIO_E_BADARG, "tcgen05 splat forward does not support this shape%s%s");
     if (impl == HELIO_SPLAT_TC || (impl == HELIO_SPLAT_AUTO && tc_ok && splat_tc_fwd_preferred(B, N, R))) {
-        HELIO_CUDA_OK(splat_tc_fwd(params, img, B, N, R, width, height, d->sms, (cudaStream_t)stream, tc_pair_mode()));
+        static const int split = []() {   // tuning / A-B switch: producer warps per operand slab (0 = auto)
+            const char* e = std::getenv("HELIO_TC_FWD_SPLIT");
+            return e ? std::atoi(e) : 0;
+        }();
+        HELIO_CUDA_OK(splat_tc_fwd(params, img, B, N, R, width, height, d->sms, (cudaStream_t)stream, tc_pair_mode(), split));
     } else {
         HELIO_CUDA_OK(splat_fwd_simt(params, img, B, N, R, width, height, d->sms, (cudaStream_t)stream));
     }

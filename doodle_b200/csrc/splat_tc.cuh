@@ -39,7 +39,7 @@ constexpr int kTcMaxR = 1024;  // coordinate tables live in shared memory
 // ------------------------------------------------------------------------------------------------
 // pieces shared by both kernels
 // ------------------------------------------------------------------------------------------------
-template <int NT, int CG, int BROWS, int ASPLIT>
+template <int NT, int CG, int BROWS, int ASPLIT, int BSPLIT = 1>
 struct SplatTcLayout {
     static constexpr int kNT = NT;                       // UMMA N (accumulator columns)
     static constexpr int kM = 128;                       // A rows per CTA = TMEM lanes
@@ -47,7 +47,8 @@ struct SplatTcLayout {
     static constexpr int kKC = 32;                       // K per stage (one 128-byte swizzle row of tf32)
     static constexpr int kASplit = ASPLIT;               // warps sharing one 32-row slab of A (each takes kKC / ASPLIT of K)
     static constexpr int kAWarps = kM / 32 * ASPLIT;
-    static constexpr int kBWarps = kBRows / 32;
+    static constexpr int kBSplit = BSPLIT;               // same for the B operand rows
+    static constexpr int kBWarps = kBRows / 32 * BSPLIT;
     static constexpr int kMmaWarp = kAWarps + kBWarps;
     static constexpr int kEpiWarp0 = kMmaWarp + 1;
     static constexpr int kThreads = (kEpiWarp0 + 4) * 32;
@@ -203,18 +204,18 @@ struct SplatTcCtx {
 // ================================================================================================
 // forward
 // ================================================================================================
-template <int NT, int CG>
-using SplatFwdTc = SplatTcLayout<NT, CG, NT / CG, 1>;
+template <int NT, int CG, int PS>
+using SplatFwdTc = SplatTcLayout<NT, CG, NT / CG, PS, PS>;
 
 // Producer mapping: a warp owns 32 operand rows (image rows for A, image columns for B); a lane owns
 // 4 consecutive heliostats of the stage (one 16-byte chunk of the K-major row) and walks 8 of the
 // rows, so the footprint parameters sit in registers (loaded once per stage, prefetched one stage
 // ahead) and every warp store writes four full 128-byte rows of the swizzled tile, conflict-free.
-template <int NT, int CG>
-__global__ void __launch_bounds__(SplatFwdTc<NT, CG>::kThreads, 1)
+template <int NT, int CG, int PS>
+__global__ void __launch_bounds__(SplatFwdTc<NT, CG, PS>::kThreads, 1)
 splat_fwd_tc_kernel(const float4* __restrict__ params, float* __restrict__ img, int N, int R, Axis ax, Axis ay,
                     int tiles_i, int tiles_j, int num_tiles) {
-    using C = SplatFwdTc<NT, CG>;
+    using C = SplatFwdTc<NT, CG, PS>;
     extern __shared__ uint8_t smem_raw[];
     SplatTcCtx<C, CG> cx;
     cx.setup(smem_raw, R, ax, ay);
@@ -227,17 +228,26 @@ splat_fwd_tc_kernel(const float4* __restrict__ params, float* __restrict__ img, 
 
     if (warp < C::kMmaWarp) {
         // ================= producers =================
-        // lane = (row subgroup rs = lane >> 3, K chunk ch = lane & 7): per step a warp covers 4 operand rows x
-        // 32 heliostats, each lane evaluating its 4 heliostats for one row and storing them as one 16-byte chunk.
-        static_assert(C::kASplit == 1, "forward producers take whole K stages");
+        // PS warps share a 32-row slab and each takes 32 / PS heliostats of a stage (PS = 2 halves the latency of a
+        // producer warp per stage, which is what bounds narrow tiles).  lane = (row subgroup rs, K chunk ch): per step
+        // a warp covers kRS rows x 32 / PS heliostats, each lane evaluating its 4 heliostats for one row and storing
+        // them as one 16-byte chunk of the swizzled row.
+        constexpr int PSX = C::kASplit;                  // = kBSplit
+        constexpr int kCh = 8 / PSX;                     // 16-byte chunks per warp and row
+        constexpr int kRS = 32 / kCh;                    // rows per step: 4 (PS = 1) or 8 (PS = 2)
+        constexpr int kSteps = 32 / kRS;
+        static_assert(PSX == 1 || PSX == 2, "producer split");
         const bool isA = warp < C::kAWarps;
-        const int wrow = (isA ? warp : warp - C::kAWarps) * 32;          // first operand row of this warp (CTA-local)
-        const int rs = lane >> 3, ch = lane & 7;
+        const int pw = isA ? warp : warp - C::kAWarps;                   // producer index inside its operand
+        const int wrow = (pw / PSX) * 32;                                // first operand row of this warp (CTA-local)
+        const int rs = lane / kCh, ch = (pw % PSX) * kCh + lane % kCh;
         const uint32_t region = (isA ? 0u : 2u * C::kABytes) + (uint32_t)(wrow >> 3) * 1024u;
         const uint32_t lo_delta = isA ? C::kABytes : C::kBBytes;
-        // rows visited by this lane: wrow + 4*step + rs, step = 0..7; (row & 7) = 4*(step & 1) + rs
-        const uint32_t off_even = (uint32_t)rs * 128u + (((uint32_t)ch ^ (uint32_t)rs) << 4);
-        const uint32_t off_odd = (uint32_t)(rs + 4) * 128u + (((uint32_t)ch ^ (uint32_t)(rs + 4)) << 4);
+        // rows visited by this lane: wrow + kRS*step + rs
+        auto row_off = [&](int st) -> uint32_t {
+            const uint32_t row = (uint32_t)(kRS * st + rs);
+            return (row >> 3) * 1024u + (row & 7u) * 128u + ((((uint32_t)ch) ^ (row & 7u)) << 4);
+        };
         uint32_t it = 0;                             // global stage counter
         for (int tile = group; tile < num_tiles; tile += ngroups) {
             const int b = tile / tiles_per_img, t = tile % tiles_per_img;
@@ -246,9 +256,9 @@ splat_fwd_tc_kernel(const float4* __restrict__ params, float* __restrict__ img, 
             // Gaussians and leave the stage bytes as they are (accumulator rows and columns are independent)
             const bool dead = g0 >= R;
             const uint32_t tab = (isA ? cx.sX_u : cx.sY_u) + (uint32_t)(g0 + rs) * 4u;
-            float xr[8];
+            float xr[kSteps];
 #pragma unroll
-            for (int st = 0; st < 8; ++st) xr[st] = tc::lds_f32(tab + 16u * st);
+            for (int st = 0; st < kSteps; ++st) xr[st] = tc::lds_f32(tab + 4u * kRS * st);
             const float4* pb = params + (size_t)b * N;
             // this lane's 4 heliostats of the stage, prefetched one stage ahead as raw float4 (index clamped so the
             // load never needs a select: nothing touches the loaded registers until the next stage decodes them)
@@ -275,7 +285,7 @@ splat_fwd_tc_kernel(const float4* __restrict__ params, float* __restrict__ img, 
                 const uint32_t base = cx.smem_u + (uint32_t)(s * C::kStageBytes) + region;
                 if (!dead)
 #pragma unroll
-                for (int st = 0; st < 8; ++st) {
+                for (int st = 0; st < kSteps; ++st) {
                     float hi[4], lo[4];
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
@@ -283,7 +293,7 @@ splat_fwd_tc_kernel(const float4* __restrict__ params, float* __restrict__ img, 
                         const float v = ex2(fmaf(d * nk2[e], d, la[e]));
                         tc::split_tf32(v, hi[e], lo[e]);
                     }
-                    const uint32_t dst = base + (uint32_t)(st >> 1) * 1024u + ((st & 1) ? off_odd : off_even);
+                    const uint32_t dst = base + row_off(st);
                     tc::sts_v4(dst, hi[0], hi[1], hi[2], hi[3]);
                     tc::sts_v4(dst + lo_delta, lo[0], lo[1], lo[2], lo[3]);
                 }
@@ -373,27 +383,37 @@ inline cudaError_t launch_tc_groups(Kernel kernel, long long num_tiles, int num_
     return cudaLaunchKernelEx(&cfg, kernel, args...);
 }
 
-template <int NT, int CG>
+template <int NT, int CG, int PS>
 inline cudaError_t launch_splat_fwd_tc(const float* params, float* img, int B, int N, int R, float width, float height,
                                        int num_sms, cudaStream_t st) {
-    using C = SplatFwdTc<NT, CG>;
+    using C = SplatFwdTc<NT, CG, PS>;
     const int tiles_i = (R + C::kM * CG - 1) / (C::kM * CG), tiles_j = (R + NT - 1) / NT;
     const long long num_tiles = (long long)B * tiles_i * tiles_j;
     if (num_tiles > 0x7fffffffLL) return cudaErrorInvalidValue;
-    return launch_tc_groups<CG>(splat_fwd_tc_kernel<NT, CG>, num_tiles, num_sms, C::kThreads, C::kSmemBytes, st,
+    return launch_tc_groups<CG>(splat_fwd_tc_kernel<NT, CG, PS>, num_tiles, num_sms, C::kThreads, C::kSmemBytes, st,
                                 reinterpret_cast<const float4*>(params), img, N, R, make_axis(width, R), make_axis(height, R),
                                 tiles_i, tiles_j, (int)num_tiles);
 }
 
 // pair = 0: auto (CTA pairs for images taller than 128 rows), 1: single CTA, 2: CTA pairs
+// split = producer warps per 32-row operand slab (1 or 2; 0 = auto)
 inline cudaError_t splat_tc_fwd(const float* params, float* img, int B, int N, int R, float width, float height, int num_sms,
-                                cudaStream_t st, int pair = 0) {
+                                cudaStream_t st, int pair = 0, int split = 0) {
     if (R > 128) {
-        if (pair != 1 && num_sms >= 2) return launch_splat_fwd_tc<256, 2>(params, img, B, N, R, width, height, num_sms, st);
-        return launch_splat_fwd_tc<256, 1>(params, img, B, N, R, width, height, num_sms, st);
+        if (pair != 1 && num_sms >= 2) {
+            if (split == 2) return launch_splat_fwd_tc<256, 2, 2>(params, img, B, N, R, width, height, num_sms, st);
+            return launch_splat_fwd_tc<256, 2, 1>(params, img, B, N, R, width, height, num_sms, st);
+        }
+        return launch_splat_fwd_tc<256, 1, 1>(params, img, B, N, R, width, height, num_sms, st);
     }
-    if (R > 64) return launch_splat_fwd_tc<128, 1>(params, img, B, N, R, width, height, num_sms, st);
-    return launch_splat_fwd_tc<64, 1>(params, img, B, N, R, width, height, num_sms, st);
+    if (R > 64) {
+        if (split == 2) return launch_splat_fwd_tc<128, 1, 2>(params, img, B, N, R, width, height, num_sms, st);
+        return launch_splat_fwd_tc<128, 1, 1>(params, img, B, N, R, width, height, num_sms, st);
+    }
+    // measured on B200: two producer warps per slab only pay off for the 64-wide tile (-11 % at N = 5000; the wider
+    // tiles are bound by shared-memory bandwidth, not producer latency, and lose 8-10 %)
+    if (split == 1) return launch_splat_fwd_tc<64, 1, 1>(params, img, B, N, R, width, height, num_sms, st);
+    return launch_splat_fwd_tc<64, 1, 2>(params, img, B, N, R, width, height, num_sms, st);
 }
 
 // ================================================================================================
