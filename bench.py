@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--B", type=int, default=WORKLOAD["B"], help="suns per GPU")
     ap.add_argument("--splat", default="auto", choices=["auto", "simt", "tc"])
     ap.add_argument("--cache-target", action="store_true", help="cache the target render (exact; off = reference-faithful)")
+    ap.add_argument("--e2e-serial", action="store_true", help="e2e arm with caller-side copies instead of the host-action step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-small-field", action="store_true", help="skip the N=50, R=128, B=25 env-steps/s side measurement")
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget for the cpu_baseline sample")
@@ -379,9 +380,13 @@ def main_ours(args):
     h_metrics = torch.empty(4, dtype=torch.float32).pin_memory()
 
     def e2e_step():
-        a = h_action.to(dev, non_blocking=True)
-        g, m = one_step(a)
-        h_grad.copy_(g, non_blocking=True)
+        if args.e2e_serial:                            # plain caller-side copies around a device step
+            a = h_action.to(dev, non_blocking=True)
+            g, m = one_step(a)
+            h_grad.copy_(g, non_blocking=True)
+        else:                                          # public API with a host action: env.step overlaps the copies
+            g, m = one_step(h_action)                  # g = action.grad, already in (pinned) host memory
+            assert g.device.type == "cpu"
         h_metrics.copy_(torch.stack([m["mse"], m["dist"], m["bound"], m["alignment_loss"]]).detach(), non_blocking=True)
         torch.cuda.current_stream().synchronize()      # the caller reads the result every step
 
@@ -449,7 +454,9 @@ def main_ours(args):
                             renders_per_step="noisy fwd+bwd, target fwd" if not args.cache_target else "noisy fwd+bwd"),
                 clocks=clocks,
                 e2e=dict(value=evals_step / (ms_e2e * 1e-3), unit=UNIT, ms_per_step=ms_e2e,
-                         h2d_bytes_per_step=h_action.numel() * 4, d2h_bytes_per_step=h_grad.numel() * 4 + 16),
+                         h2d_bytes_per_step=h_action.numel() * 4, d2h_bytes_per_step=h_grad.numel() * 4 + 16,
+                         path="caller-side copies around a device step" if args.e2e_serial else
+                              "env.step(host action): H2D under the target render, gradient D2H under the backward slices"),
                 gpu_launches=launches, roofline=roofline, cpu_baseline=cpu_baseline, small_field=small)
     print(json.dumps(line))
     if world > 1:

@@ -11,6 +11,7 @@ from .env import (HelioEnv, azimuth_elevation_to_primary_direction, make_distanc
                   sample_cone_directions)
 from .field import HelioField  # noqa: F401
 from .graphs import GraphedStep  # noqa: F401
+from .layers import CenterOfMass2D  # noqa: F401
 
-__all__ = ["HelioField", "HelioEnv", "GraphedStep", "HelioLibError", "SPLAT_AUTO", "SPLAT_SIMT", "SPLAT_TC",
+__all__ = ["HelioField", "HelioEnv", "GraphedStep", "CenterOfMass2D", "HelioLibError", "SPLAT_AUTO", "SPLAT_SIMT", "SPLAT_TC",
            "azimuth_elevation_to_primary_direction", "sample_cone_directions", "make_distance_maps"]

@@ -22,6 +22,7 @@ EXPORTS = (
     "helio_geom_bwd", "helio_splat_fwd", "helio_splat_bwd", "helio_image_max", "helio_loss_fwd", "helio_loss_bwd",
     "helio_profile_enable", "helio_profile_count", "helio_profile_get",
     "helio_distance_maps_workspace_bytes", "helio_distance_maps",
+    "helio_com_fwd", "helio_com_bwd",
     "helio_loss_bwd_packed", "helio_loss_pack", "helio_step_fwd", "helio_step_bwd",
 )
 
@@ -75,6 +76,10 @@ def _declare(lib):
     lib.helio_distance_maps_workspace_bytes.argtypes = [i, i]
     lib.helio_distance_maps.restype = i
     lib.helio_distance_maps.argtypes = [p, i, i, f, p, p, i64, p]
+    lib.helio_com_fwd.restype = i
+    lib.helio_com_fwd.argtypes = [p, i, i, i, f, p, p, p]
+    lib.helio_com_bwd.restype = i
+    lib.helio_com_bwd.argtypes = [p, p, p, i, i, i, f, p, p]
     lib.helio_geom_workspace_bytes.restype = i64
     lib.helio_geom_workspace_bytes.argtypes = [i, i]
     lib.helio_geom_fwd.restype = i

@@ -4,6 +4,7 @@
 #include <mutex>
 #include <vector>
 
+#include "com.cuh"
 #include "edt.cuh"
 #include "geom.cuh"
 #include "loss.cuh"
@@ -310,6 +311,35 @@ HELIO_API int helio_loss_pack(const float* per_img, int B, float* packed, void* 
     HELIO_REQUIRE(B > 0, "B must be positive");
     KernelTimer timer("loss_pack", stream);
     loss_pack_kernel<<<1, kLossThreads, 0, (cudaStream_t)stream>>>(per_img, B, packed);
+    HELIO_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+HELIO_API int helio_com_fwd(const float* img, int B, int H, int W, float eps, float* coords, float* sums, void* stream) {
+    const DeviceInfo* d = nullptr;
+    if (int rc = require_device(&d)) return rc;
+    HELIO_REQUIRE(img && coords, "null pointer");
+    HELIO_REQUIRE(B > 0 && H > 0 && W > 0, "B, H, W must be positive");
+    int slices = 1;
+    while (slices < 8 && (long long)B * slices < 8LL * d->sms && H / (2 * slices) >= kLossThreads / 32) slices *= 2;
+    KernelTimer timer("com_fwd", stream);
+    HELIO_CUDA_OK(launch_image_clusters(com_fwd_kernel, B, slices, (cudaStream_t)stream, img, H, W, slices, eps, coords, sums));
+    return 0;
+}
+
+HELIO_API int helio_com_bwd(const float* img, const float* sums, const float* g_coords, int B, int H, int W, float eps,
+                  float* g_img, void* stream) {
+    const DeviceInfo* d = nullptr;
+    if (int rc = require_device(&d)) return rc;
+    HELIO_REQUIRE(img && sums && g_coords && g_img, "null pointer");
+    HELIO_REQUIRE(B > 0 && H > 0 && W > 0, "B, H, W must be positive");
+    int slices = (H + kLossThreads / 32 - 1) / (kLossThreads / 32);
+    const int want = (16 * d->sms + B - 1) / B;
+    if (slices > want) slices = want;
+    if (slices < 1) slices = 1;
+    KernelTimer timer("com_bwd", stream);
+    com_bwd_kernel<<<(unsigned)((long long)B * slices), kLossThreads, 0, (cudaStream_t)stream>>>(img, sums, g_coords, H, W,
+                                                                                              slices, eps, g_img);
     HELIO_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -13,6 +13,10 @@ Differences, all opt-in or bug-compatible:
   * ``fused_step`` (keyword-only, default True): ``step`` runs as one C-ABI call forward and one backward
     (helio_step_fwd / helio_step_bwd: the same kernels, far less host time for small fields); the
     error-mask and exponential-risk variants take the composed path;
+  * a HOST action (CPU tensor or np.ndarray, which the reference accepts too, :411-412) is copied in on a side
+    stream while the target renders, and its gradient is returned in pinned host memory, copied out slice by slice
+    under the backward kernels (functional.HostStepFn); ``obs['aux']`` is then built from the device copy (no
+    autograd link to the host action);
   * ``cache_target`` (keyword-only extension, default False = re-render the target every step as
     the reference does, test_environment.py:429-435).  The target only depends on ``sun_pos``, so
     caching it is exact.
@@ -28,7 +32,7 @@ import torch.nn.functional as F
 from scipy.ndimage import distance_transform_edt
 
 from .field import HelioField
-from .functional import ImageLossFn, StepFn, _cf, image_max, require_cuda
+from .functional import HostStepFn, ImageLossFn, StepFn, _cf, image_max, require_cuda
 from .functional import distance_maps as _distance_maps_cuda
 
 try:  # gymnasium is optional: only Env / spaces.Box / spaces.Dict are touched (test_environment.py:11-12)
@@ -168,6 +172,8 @@ class HelioEnv(_EnvBase):
         self.cache_target = cache_target
         self.check_finite = check_finite
         self.fused_step = fused_step
+        self.host_chunks = 4                           # backward slices when the action lives in host memory
+        self._copy_stream = None
         self.distance_maps_impl = distance_maps_impl   # "auto"/"cuda": GPU EDT; "scipy": the reference's host path
         self._target_cache = None
 
@@ -230,8 +236,9 @@ class HelioEnv(_EnvBase):
         self._target_cache = None
         self.ref_field.init_actions(self.sun_pos)
         with torch.no_grad():
-            ideal_normals = self.ref_field.calculate_ideal_normals(self.sun_pos)
-            timg, _ = self.ref_field.render(self.sun_pos, self.ref_field.initial_action, ideal_normals)
+            out = self.ref_field._render_full(self.sun_pos, self.ref_field.initial_action, want_aux=True)
+            timg = out.img
+        self._ideal_of_suns = out.ideal          # K1's ideal normals: a function of the suns only (host-action path)
         self.distance_maps = make_distance_maps(timg, impl=self.distance_maps_impl)
         self.ref_min = torch.min(timg)
         self.ref_max = torch.max(timg)
@@ -272,11 +279,29 @@ class HelioEnv(_EnvBase):
 
     def step(self, action):
         """obs, metrics, monitor = step(action)   (:402-516).  action: [B, 3N] or [B, N, 3]."""
-        if isinstance(action, np.ndarray):
-            action = torch.tensor(action, dtype=torch.float32, device=self.device)
         B, N, R = self.batch_size, self.num_heliostats, self.resolution
+        fused = self.fused_step and not self.use_error_mask and not self.exponential_risk
+        if isinstance(action, np.ndarray):                                           # :411-412
+            action = torch.from_numpy(np.ascontiguousarray(action, dtype=np.float32))
+        if not fused and action.device.type == "cpu":
+            action = action.to(self.device)
+        action_dev = action
 
-        if self.fused_step and not self.use_error_mask and not self.exponential_risk:
+        if fused and action.device.type == "cpu":
+            # host-resident action: copies overlapped with the target render / the backward slices (HostStepFn)
+            nf = self.noisy_field
+            act = action if action.dtype == torch.float32 else action.float()
+            cached = self._target_cache if self.cache_target and self._target_cache is not None else (None, None)
+            if self._copy_stream is None:
+                self._copy_stream = torch.cuda.Stream(device=nf.device)
+            img, packed, _actual, refl, ideal_normals, bounds, angles, per_img, target, tx, action_dev = HostStepFn.apply(
+                act.contiguous(), self.sun_pos, _cf(nf._select_errors(B)), nf.heliostat_positions, self.distance_maps, nf.scene(),
+                nf._geom_workspace(B), R, nf.splat_impl, nf.splat_impl if nf.splat_impl_bwd is None else nf.splat_impl_bwd,
+                cached[0], cached[1], self._ideal_of_suns, self._copy_stream, self.host_chunks)
+            if self.cache_target and self._target_cache is None:
+                self._target_cache = (target, tx)
+            out = SimpleNamespace(refl=refl, bounds=bounds, angles=angles)
+        elif fused:
             nf = self.noisy_field
             act = action.to(device=nf.device, dtype=torch.float32)
             normals = act.reshape(B, N, 3).contiguous()
@@ -294,7 +319,7 @@ class HelioEnv(_EnvBase):
             target, tx = self._target(ideal_normals)
             per_img = ImageLossFn.apply(img, target, self.distance_maps, tx)             # K4: [B,3]
             packed = None
-        aux = torch.cat([self.sun_pos.detach(), action.flatten(1)], dim=1)
+        aux = torch.cat([self.sun_pos.detach(), action_dev.flatten(1)], dim=1)
         avg_error_per_heatmap = per_img[:, 2] / float(R * R)
 
         if packed is None:

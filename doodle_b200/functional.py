@@ -298,3 +298,100 @@ class StepFn(torch.autograd.Function):
         global _LAUNCHES
         _LAUNCHES += (1 if need_img else 0) + (1 if need_splat else 0)
         return (g_action,) + (None,) * 11
+
+
+class HostStepFn(torch.autograd.Function):
+    """StepFn for an action that lives in HOST memory (the reference accepts host actions too: np.ndarray,
+    test_environment.py:411-412), with the transfers overlapped instead of serialised:
+
+      forward : the host->device copy of the action runs on a side stream while the main stream renders the target
+                (which depends on the suns only); the noisy render starts when the copy lands;
+      backward: runs in ``chunks`` slices of the sun batch; the device->host copy of a slice's action gradient
+                overlaps the next slice's kernels.  Returns the gradient as a pinned HOST tensor.
+
+    Same kernels, same numbers as StepFn (the per-sun slices are independent; packed sums are formed over the whole
+    batch in the forward)."""
+
+    @staticmethod
+    def forward(ctx, action_host, sun, errs, helio, dmaps, scene, workspace, R, impl, impl_bwd, target, tx, ideal, copy_stream,
+                chunks: int):
+        lib = _lib.load()
+        B, N = sun.shape[0], helio.shape[0]
+        dev = sun.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        main = torch.cuda.current_stream(dev)
+        action = torch.empty(B, N, 3, **f32)
+        copy_stream.wait_stream(main)                    # `action` is allocated on main's pool: order its first use
+        with torch.cuda.stream(copy_stream):
+            action.copy_(action_host.reshape(B, N, 3), non_blocking=True)
+            landed = torch.cuda.Event()
+            landed.record(copy_stream)
+        params = torch.empty(B, N, 4, **f32)
+        actual, refl, ideal_out = torch.empty(B, N, 3, **f32), torch.empty(B * N, 3, **f32), torch.empty(B, N, 3, **f32)
+        bounds, angles = torch.empty(B, N, **f32), torch.empty(B, N, **f32)
+        img = torch.empty(B, R, R, **f32)
+        per_img, packed = torch.empty(B, 3, **f32), torch.empty(4, **f32)
+        global _LAUNCHES
+        with _Call("step_fwd_host", dev):
+            if target is None:                           # target render first: it does not need the action
+                target, tx = torch.empty(B, R, R, **f32), torch.empty(B, **f32)
+                scratch = torch.empty(B * N * 10, **f32)
+                rc = lib.helio_geom_fwd(C.byref(scene), _ptr(helio), _ptr(sun), _ptr(ideal), None, B, N, _ptr(scratch),
+                                        _ptr(scratch[4 * B * N:]), _ptr(scratch[7 * B * N:]), None, None, None, None, None, 0, _stream())
+                _lib.check(rc, "helio_geom_fwd")
+                _lib.check(lib.helio_splat_fwd(_ptr(scratch), B, N, R, scene.width, scene.height, _ptr(target), impl, _stream()), "helio_splat_fwd")
+                _lib.check(lib.helio_image_max(_ptr(target), B, R, _ptr(tx), _stream()), "helio_image_max")
+                _LAUNCHES += 3
+            main.wait_event(landed)
+            rc = lib.helio_step_fwd(
+                C.byref(scene), _ptr(helio), _ptr(sun), _ptr(action), _ptr(errs), _ptr(dmaps), B, N, R, impl, 0,
+                _ptr(params), _ptr(actual), _ptr(refl), _ptr(ideal_out), _ptr(bounds), _ptr(angles), _ptr(img), _ptr(target),
+                _ptr(tx), _ptr(per_img), _ptr(packed), None, None, None,
+                _ptr(workspace), workspace.numel() * workspace.element_size(), _stream())
+        _lib.check(rc, "helio_step_fwd")
+        _LAUNCHES += 3
+        ctx.save_for_backward(action, sun, errs, helio, dmaps, params, img, target, tx)
+        ctx.cfg = (scene, R, impl_bwd, copy_stream, max(1, min(int(chunks), B)), action_host.shape, action_host.is_pinned())
+        ctx.set_materialize_grads(False)
+        action_dev = action.view(B, N, 3)             # handed back (no gradient) so that obs['aux'] can be built on the device
+        ctx.mark_non_differentiable(ideal_out, target, tx, action_dev)
+        return img, packed, actual, refl, ideal_out, bounds, angles, per_img, target, tx, action_dev
+
+    @staticmethod
+    def backward(ctx, g_img_in, g_packed, g_actual, g_refl, g_ideal, g_bounds, g_angles, g_per_img, g_target, g_tx, g_adev):
+        lib = _lib.load()
+        action, sun, errs, helio, dmaps, params, img, target, tx = ctx.saved_tensors
+        scene, R, impl, copy_stream, chunks, host_shape, pinned = ctx.cfg
+        B, N = sun.shape[0], helio.shape[0]
+        dev = action.device
+        gs = [None if g is None else _cf(g) for g in (g_packed, g_per_img, g_img_in, g_actual, g_refl, g_bounds, g_angles)]
+        need_img = gs[0] is not None or gs[1] is not None
+        need_splat = need_img or gs[2] is not None
+        g_action = torch.empty_like(action)
+        g_img = torch.empty_like(img) if need_img else None
+        moments = torch.empty_like(params) if need_splat else None
+        h_grad = torch.empty(B, N, 3, dtype=torch.float32, pin_memory=pinned)
+        main = torch.cuda.current_stream(dev)
+        sl = lambda t, b0, nb: None if t is None else t.narrow(0, b0, nb)
+        global _LAUNCHES
+        per = (B + chunks - 1) // chunks
+        with _Call("step_bwd_host", dev):
+            for b0 in range(0, B, per):
+                nb = min(per, B - b0)
+                refl_g = None if gs[4] is None else gs[4].view(B, N, 3).narrow(0, b0, nb)
+                rc = lib.helio_step_bwd(
+                    C.byref(scene), _ptr(helio), _ptr(sl(sun, b0, nb)), _ptr(sl(action, b0, nb)), _ptr(sl(errs, b0, nb)),
+                    _ptr(sl(params, b0, nb)), _ptr(sl(img, b0, nb)), _ptr(sl(target, b0, nb)), _ptr(sl(dmaps, b0, nb)),
+                    _ptr(sl(tx, b0, nb)), nb, N, R, impl, _ptr(gs[0]), _ptr(sl(gs[1], b0, nb)), _ptr(sl(gs[2], b0, nb)),
+                    _ptr(sl(gs[3], b0, nb)), _ptr(refl_g), _ptr(sl(gs[5], b0, nb)), _ptr(sl(gs[6], b0, nb)),
+                    _ptr(sl(g_img, b0, nb)), _ptr(sl(moments, b0, nb)), _ptr(sl(g_action, b0, nb)), _stream())
+                _lib.check(rc, "helio_step_bwd")
+                _LAUNCHES += (1 if need_img else 0) + (1 if need_splat else 0) + (1 if b0 else 0)
+                done = torch.cuda.Event()
+                done.record(main)
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(done)
+                    h_grad.narrow(0, b0, nb).copy_(g_action.narrow(0, b0, nb), non_blocking=True)
+        main.wait_stream(copy_stream)                 # g_action is freed on main: keep the allocator's ordering
+        copy_stream.synchronize()                     # the caller owns a host tensor: it must be complete
+        return (h_grad.view(host_shape),) + (None,) * 14

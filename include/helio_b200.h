@@ -157,6 +157,16 @@ HELIO_API int helio_loss_bwd(const float* img, const float* target, const float*
                    const float* g_per_img, const float* g_img_in, int B, int R, float* g_img,
                    void* stream);
 
+/* Centre of mass of each image: CenterOfMass2D.forward (layers/center_of_mass.py:21-60), the encoder
+ * feed of train_with_env_com_trunc_advantage_ttt.py:42-53.  img[B][H][W] (row i = y, column j = x);
+ * coords[B][2] = (sum w j, sum w i) / (sum w + eps) with w = max(img, 0), or (-1, -1) when sum w <= 0;
+ * sums[B][3] = {sum w, sum w j, sum w i} (may be NULL; needed by helio_com_bwd). */
+HELIO_API int helio_com_fwd(const float* img, int B, int H, int W, float eps, float* coords, float* sums, void* stream);
+/* its adjoint: g_img[i][j] = [img >= 0] (g_x (j - x_com) + g_y (i - y_com)) / (sum w + eps), zero for
+ * images without mass.  g_coords[B][2]. */
+HELIO_API int helio_com_bwd(const float* img, const float* sums, const float* g_coords, int B, int H, int W,
+                  float eps, float* g_img, void* stream);
+
 /* helio_loss_bwd with the batch-wide gradients folded in: {g0,g1,g2} = g_per_img[b] (may be NULL) +
  * {g_packed[0], g_packed[1], 0} (may be NULL), where g_packed[4] (device) are the upstream grads of
  * helio_step_fwd's packed sums. */

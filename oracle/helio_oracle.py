@@ -458,3 +458,34 @@ def azimuth_elevation_to_direction(az_deg: float, el_deg: float) -> np.ndarray:
     az, el = math.radians(az_deg), math.radians(el_deg)
     vec = np.array([math.cos(el) * math.cos(az), math.cos(el) * math.sin(az), math.sin(el)], dtype=np.float32)
     return vec / np.sqrt((vec * vec).sum(dtype=np.float32))
+
+
+# ----------------------------------------------------------------------------
+# centre of mass (the COM trainer's encoder feed)
+# ----------------------------------------------------------------------------
+def center_of_mass(x, eps=1e-12, g_coords=None, dtype=np.float32):
+    """layers/center_of_mass.py:21-60 (CenterOfMass2D.forward) and its autograd.
+
+    x [B,H,W] -> coords [B,2] = (x_com, y_com), origin top-left, x = column, y = row; (-1,-1) when the
+    image has no mass.  With ``g_coords`` [B,2] also returns dL/dx [B,H,W] (clamp_min passes the gradient
+    where x >= 0; the (-1,-1) overwrite kills it for mass-free images)."""
+    x = _f(x, dtype)
+    B, H, W = x.shape
+    w = np.maximum(x, dtype(0))                                                    # :37
+    yy, xx = np.meshgrid(np.arange(H, dtype=dtype), np.arange(W, dtype=dtype), indexing="ij")   # :40-44
+    w_sum = w.sum(axis=(1, 2), dtype=dtype)                                        # :47
+    x_wsum = (w * xx).sum(axis=(1, 2), dtype=dtype)
+    y_wsum = (w * yy).sum(axis=(1, 2), dtype=dtype)
+    den = w_sum + dtype(eps)
+    coords = np.stack([x_wsum / den, y_wsum / den], axis=-1).astype(dtype)         # :52-55
+    no_mass = w_sum <= 0                                                           # :58-60
+    coords[no_mass] = dtype(-1.0)
+    if g_coords is None:
+        return coords
+    g = _f(g_coords, dtype)
+    gx = np.where(no_mass, dtype(0), g[:, 0] / den)[:, None, None]
+    gy = np.where(no_mass, dtype(0), g[:, 1] / den)[:, None, None]
+    xc = (x_wsum / den)[:, None, None]
+    yc = (y_wsum / den)[:, None, None]
+    g_x = (gx * (xx[None] - xc) + gy * (yy[None] - yc)) * (x >= 0)
+    return coords, g_x.astype(dtype)

@@ -148,6 +148,29 @@ def host_case(ref_env):
                         dirs2=npy(dirs2), imgs=npy(imgs), dmaps=npy(dm))
 
 
+def com_case():
+    """CenterOfMass2D (layers/center_of_mass.py) forward + autograd on seeded images, incl. a mass-free image,
+    negative pixels (clamped), a (B,1,H,W) input and a non-square image."""
+    sys.path.insert(0, REF)
+    from layers.center_of_mass import CenterOfMass2D
+    torch.manual_seed(31)
+    com = CenterOfMass2D()
+    out = {}
+    for name, shape in (("sq", (5, 24, 24)), ("rect", (3, 1, 10, 37))):
+        x = torch.rand(*shape)
+        flat = x.view(shape[0], shape[-2], shape[-1])
+        flat[1] = 0.0                                   # no mass -> (-1,-1), zero gradient
+        flat[2] -= 0.5                                  # negative pixels are clamped to zero mass
+        flat[0, 3, 4] = 0.0                             # clamp_min passes the gradient at exactly 0
+        x = x.clone().requires_grad_(True)
+        coords = com(x)
+        w = torch.randn_like(coords)
+        g, = torch.autograd.grad((coords * w).sum(), x)
+        out.update({f"{name}_x": npy(x), f"{name}_coords": npy(coords), f"{name}_w": npy(w), f"{name}_grad": npy(g)})
+    np.savez_compressed(os.path.join(OUT, "com.npz"), **out)
+    print("com: ", out["sq_coords"][:3].tolist())
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref_field, ref_env = import_reference()
@@ -190,6 +213,7 @@ def main():
     env_case(ref_env, "mask", 23, N=5, R=16, B=10, sigma_scale=0.1, err_mrad=90.0, helio_fn=readme, use_error_mask=True)
     env_case(ref_env, "exprisk", 24, N=5, R=16, B=3, sigma_scale=0.1, err_mrad=400.0, helio_fn=readme, exponential_risk=True)
     host_case(ref_env)
+    com_case()
 
 
 if __name__ == "__main__":

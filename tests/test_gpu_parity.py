@@ -157,6 +157,33 @@ def test_fused_step_equals_composed_step():
         assert rel_err(g1[k].cpu().numpy(), g2[k].cpu().numpy()) < 2e-6, k
 
 
+@pytest.mark.parametrize("cache", [False, True])
+def test_host_action_step_equals_device_step(cache):
+    """env.step on a HOST action (pinned CPU tensor or np.ndarray, test_environment.py:411-412): overlapped copies,
+    sliced backward -- same images, metrics and gradients as the device-resident call, gradient delivered on the host."""
+    g = load_golden("env_trainer")
+    env = _env_from_golden(g, cache_target=cache)
+    env.distance_maps = _t(g["distance_maps"])
+    env.host_chunks = 3                                        # 5 suns -> slices of 2, 2, 1
+    a_dev = _t(g["action"]).requires_grad_(True)
+    obs_d, m_d, mon_d = env.step(a_dev)
+    loss_d = m_d["mse"] + 0.01 * m_d["dist"] + m_d["bound"] + m_d["alignment_loss"]
+    gd, = torch.autograd.grad(loss_d, a_dev)
+    for rep in range(2):
+        a_host = torch.as_tensor(g["action"]).pin_memory().requires_grad_(True)
+        obs_h, m_h, mon_h = env.step(a_host)
+        assert torch.equal(obs_h["img"], obs_d["img"]) and torch.equal(obs_h["aux"], obs_d["aux"])
+        for k in m_d:
+            assert torch.equal(m_h[k].detach(), m_d[k].detach()), k
+        for k in ("reflected_rays", "ideal_normals", "all_bounds", "mae_image", "alignment_errors"):
+            assert torch.equal(mon_h[k], mon_d[k]), k
+        (m_h["mse"] + 0.01 * m_h["dist"] + m_h["bound"] + m_h["alignment_loss"]).backward()
+        assert a_host.grad.device.type == "cpu" and a_host.grad.shape == a_host.shape
+        assert torch.equal(a_host.grad, gd.cpu())
+    obs_n, m_n, _ = env.step(g["action"])                      # np.ndarray action, no gradient
+    assert torch.equal(obs_n["img"], obs_d["img"]) and not m_n["mse"].requires_grad
+
+
 def test_graphed_step_replays_eager_step():
     """CUDA-graph capture of step + backward: replays must reproduce the eager results bit for
     bit at new actions, which also proves that no entry point allocates or synchronises."""
@@ -216,6 +243,37 @@ def test_gpu_distance_maps_edge_cases():
         got = make_distance_maps(imgs, thr=thr, impl="cuda")
         ref = make_distance_maps(imgs, thr=thr, impl="scipy")   # imgs[0] has no mask pixel: scipy's virtual-pixel result
         assert torch.equal(got, ref), (thr, float((got - ref).abs().max()))
+
+
+@pytest.mark.parametrize("name", ["sq", "rect"])
+def test_center_of_mass_matches_reference(name):
+    """doodle_b200.CenterOfMass2D (helio_com_fwd / helio_com_bwd) vs the reference layer's outputs and autograd."""
+    from doodle_b200 import CenterOfMass2D
+    g = load_golden("com")
+    x = _t(g[name + "_x"]).requires_grad_(True)
+    coords = CenterOfMass2D()(x)
+    assert coords.shape == g[name + "_coords"].shape
+    np.testing.assert_allclose(coords.detach().cpu().numpy(), g[name + "_coords"], rtol=2e-6, atol=1e-6)
+    gr, = torch.autograd.grad((coords * _t(g[name + "_w"])).sum(), x)
+    assert gr.shape == x.shape
+    assert rel_err(gr.cpu().numpy().reshape(-1), g[name + "_grad"].reshape(-1)) < 1e-5
+    assert not gr.view(x.shape[0], -1)[1].any()
+
+
+@pytest.mark.parametrize("B,H,W", [(1, 8, 8), (7, 128, 128), (3, 100, 37), (300, 64, 64), (2, 512, 512)])
+def test_center_of_mass_matches_oracle(B, H, W):
+    from doodle_b200 import CenterOfMass2D
+    torch.manual_seed(B + H)
+    x = torch.rand(B, H, W, device=_dev()) - 0.2
+    if B > 2:
+        x[1] = -1.0                                            # no mass
+    w = torch.randn(B, 2, device=_dev())
+    xr = x.clone().requires_grad_(True)
+    coords = CenterOfMass2D()(xr)
+    gr, = torch.autograd.grad((coords * w).sum(), xr)
+    c64, g64 = orc.center_of_mass(x.cpu().numpy(), g_coords=w.cpu().numpy(), dtype=np.float64)
+    np.testing.assert_allclose(coords.detach().cpu().numpy(), c64, rtol=1e-5, atol=1e-5)
+    assert rel_err(gr.cpu().numpy().reshape(-1), g64.reshape(-1)) < 1e-5
 
 
 def test_env_reset_matches_reference():

@@ -108,3 +108,17 @@ def test_fp64_and_fp32_oracles_agree():
     g32 = orc.render_backward(c32, g_img=g["w_img"])
     g64 = orc.render_backward(c64, g_img=g["w_img"])
     assert rel_err(g32, g64) < 1e-3
+
+
+@pytest.mark.parametrize("name", ["sq", "rect"])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_center_of_mass_matches_reference(name, dtype):
+    """oracle.center_of_mass vs the reference's CenterOfMass2D forward + autograd (tests/golden/com.npz)."""
+    g = load_golden("com")
+    x = g[name + "_x"]
+    x3 = x.reshape(x.shape[0], x.shape[-2], x.shape[-1])
+    coords, grad = orc.center_of_mass(x3, g_coords=g[name + "_w"], dtype=dtype)
+    np.testing.assert_allclose(coords, g[name + "_coords"], rtol=2e-6, atol=1e-6)
+    assert np.array_equal(coords[1], [-1.0, -1.0])
+    assert rel_err(grad.reshape(-1), g[name + "_grad"].reshape(-1)) < 1e-5
+    assert not grad[1].any()                                   # mass-free image: zero gradient
