@@ -1,0 +1,55 @@
+#!/usr/bin/env python3
+"""NCCL parity of the sharded env (run under torchrun with W ranks): the W rank-local slices must reproduce the
+single-process HelioEnv built from the same seed -- same suns, errors, images, global metrics and action gradients.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 scripts/dist_parity.py
+"""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+import torch.distributed as dist
+from doodle_b200 import HelioEnv
+from doodle_b200.dist import make_sharded_env, shard_bounds
+
+rank, local_rank, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(local_rank)
+dev = torch.device("cuda", local_rank)
+dist.init_process_group("nccl", device_id=dev)
+ok = True
+for (N, R, B, mask) in [(40, 64, 8 * world, False), (300, 256, 4 * world, False), (40, 64, 8 * world, True)]:
+    g = torch.Generator().manual_seed(5)
+    helio = torch.rand(N, 3, generator=g) * 10 + 80; helio[:, 2] = 0
+    kw = dict(heliostat_pos=helio.to(dev), targ_pos=torch.tensor([0., -5., 0.], device=dev), targ_area=(15., 15.),
+              targ_norm=torch.tensor([0., 1., 0.], device=dev), sigma_scale=0.05, error_scale_mrad=90.0, resolution=R, device=str(dev),
+              use_error_mask=mask)
+    env = make_sharded_env(HelioEnv, global_batch_size=B, seed=123, **kw)
+    torch.manual_seed(123)
+    full = HelioEnv(batch_size=B, **kw)                       # every rank also builds the global env (same seed)
+    lo, hi = shard_bounds(B, rank, world)
+    assert torch.equal(env.sun_pos, full.sun_pos[lo:hi])
+    # same errors and distance maps on both sides (reset draws depend on the batch size)
+    env.noisy_field.batch_error_angles_mrad = full.noisy_field.batch_error_angles_mrad[lo:hi].contiguous()
+    env.distance_maps = full.distance_maps[lo:hi].contiguous()
+    torch.manual_seed(7)
+    act_full = torch.nn.functional.normalize(full.ref_field.initial_action.view(B, N, 3) + 0.02 * torch.randn(B, N, 3, device=dev), dim=2)
+    a_full = act_full.clone().requires_grad_(True)
+    a_loc = act_full[lo:hi].clone().requires_grad_(True)
+    of, mf, _ = full.step(a_full)
+    ol, ml, _ = env.step(a_loc)
+    w = dict(mse=1.0, dist=0.01, bound=1.0, alignment_loss=1.0)
+    gf, = torch.autograd.grad(sum(w[k] * mf[k] for k in w), a_full)
+    gl, = torch.autograd.grad(sum(w[k] * ml[k] for k in w), a_loc)
+    img_ok = torch.equal(ol["img"], of["img"][lo:hi])
+    met = {k: (float(ml[k]), float(mf[k])) for k in w}
+    met_ok = all(abs(a - b) <= 2e-5 * abs(b) + 1e-9 for a, b in met.values())
+    gerr = float((gl - gf[lo:hi]).abs().max() / gf.abs().max())
+    good = img_ok and met_ok and gerr < 1e-5
+    flag = torch.tensor([1.0 if good else 0.0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print(f"N={N} R={R} B={B} mask={mask} world={world}: images equal {img_ok}, metrics {met_ok}, grad rel err {gerr:.2e} -> "
+              f"{'ok' if flag.item() == 1 else 'MISMATCH'}", flush=True)
+    ok = ok and flag.item() == 1
+dist.destroy_process_group()
+sys.exit(0 if ok else 1)
