@@ -509,3 +509,74 @@ def test_abi_errors():
     assert rc == -1 and b"impl" in lib.helio_last_error()
     with pytest.raises(_lib.HelioLibError):
         _lib.check(rc, "helio_splat_fwd")
+
+
+@pytest.mark.parametrize("N,R,B", [(5, 33, 2), (37, 100, 3), (130, 64, 2), (70, 250, 2), (300, 512, 1)])
+def test_kernels_stay_inside_their_buffers(N, R, B):
+    """Every output / scratch buffer handed to the C ABI sits between NaN-filled guard regions that must survive
+    (compute-sanitizer is not available on the GPU pool, so ragged shapes are checked this way)."""
+    import ctypes as C
+    from doodle_b200 import _lib
+    from doodle_b200._lib import Scene
+    lib = _lib.load()
+    dev = _dev()
+    G = 4096                                                   # guard floats on each side
+
+    class Guarded:
+        def __init__(self, n, fill=None):
+            self.buf = torch.full((n + 2 * G,), float("nan"), device=dev)
+            self.view = self.buf[G:G + n]
+            if fill is not None:
+                self.view.copy_(fill.reshape(-1))
+        ptr = property(lambda self: C.c_void_p(self.view.data_ptr()))
+
+        def intact(self):
+            return bool(torch.isnan(self.buf[:G]).all()) and bool(torch.isnan(self.buf[-G:]).all())
+
+        def written(self):
+            return not bool(torch.isnan(self.view).any())
+
+    torch.manual_seed(N + R)
+    sc = Scene()
+    sc.target_pos[:] = [0., -5., 0.]; sc.target_normal[:] = [0., 1., 0.]; sc.plane_u[:] = [1., 0., 0.]; sc.plane_v[:] = [0., 0., 1.]
+    sc.width, sc.height, sc.sigma_scale = 15., 15., 0.05
+    sc.bnd_targ_pos[:] = [0., -5., 0.]; sc.bnd_targ_norm[:] = [0., 1., 0.]; sc.bnd_u[:] = [1., 0., 0.]; sc.bnd_v[:] = [0., 0., 1.]
+    sc.bnd_width, sc.bnd_height = 15., 15.
+    helio = torch.rand(N, 3, device=dev) * 10 + 80; helio[:, 2] = 0
+    d = torch.nn.functional.normalize(torch.tensor([[0.5, 0.5, 0.7071]], device=dev) + 0.02 * torch.randn(B, 3, device=dev), dim=1)
+    sun = (d * 14142.0).contiguous()
+    from doodle_b200 import HelioField
+    f = HelioField(helio, torch.tensor([0., -5., 0.]), (15., 15.), torch.tensor([0., 1., 0.]), sigma_scale=0.05, resolution=R,
+                   device="cuda:0", max_batch_size=B)
+    action = (f.calculate_ideal_normals(sun) + 0.01 * torch.randn(B, N, 3, device=dev)).contiguous()
+    errs = (torch.randn(B, N, 2, device=dev) * 60).contiguous()
+    dmaps = torch.rand(B, R, R, device=dev) * 9
+    P = lambda t: C.c_void_p(t.data_ptr())
+    BN, BRR = B * N, B * R * R
+    ws_bytes = lib.helio_geom_workspace_bytes(B, N)
+    ws = torch.zeros((ws_bytes + 3) // 4, dtype=torch.int32, device=dev)
+    out = {k: Guarded(n) for k, n in dict(params=4 * BN, actual=3 * BN, refl=3 * BN, ideal=3 * BN, bounds=BN, angles=BN, img=BRR,
+                                          target=BRR, tx=B, per_img=3 * B, packed=4, tparams=4 * BN, tactual=3 * BN, trefl=3 * BN,
+                                          g_img=BRR, moments=4 * BN, g_action=3 * BN, edt=BRR, coords=2 * B, sums=3 * B, g_com=BRR).items()}
+    for impl in (2, 1):                                        # tcgen05 and CUDA-core splats
+        for o in out.values():
+            o.view.fill_(float("nan"))
+        rc = lib.helio_step_fwd(C.byref(sc), P(helio), P(sun), P(action), P(errs), P(dmaps), B, N, R, impl, 1,
+                                *[out[k].ptr for k in ("params", "actual", "refl", "ideal", "bounds", "angles", "img", "target", "tx",
+                                                       "per_img", "packed", "tparams", "tactual", "trefl")], P(ws), ws_bytes, None)
+        assert rc == 0, lib.helio_last_error()
+        g_packed = torch.tensor([1.0, 0.01, 1.0, 1.0], device=dev)
+        rc = lib.helio_step_bwd(C.byref(sc), P(helio), P(sun), P(action), P(errs), out["params"].ptr, out["img"].ptr, out["target"].ptr,
+                                P(dmaps), out["tx"].ptr, B, N, R, impl, P(g_packed), None, None, None, None, None, None,
+                                out["g_img"].ptr, out["moments"].ptr, out["g_action"].ptr, None)
+        assert rc == 0, lib.helio_last_error()
+        nb = lib.helio_distance_maps_workspace_bytes(B, R)
+        ews = torch.empty((nb + 3) // 4, dtype=torch.int32, device=dev)
+        assert lib.helio_distance_maps(out["target"].ptr, B, R, 0.5, out["edt"].ptr, P(ews), nb, None) == 0
+        assert lib.helio_com_fwd(out["img"].ptr, B, R, R, 1e-12, out["coords"].ptr, out["sums"].ptr, None) == 0
+        g_c = torch.randn(B, 2, device=dev)
+        assert lib.helio_com_bwd(out["img"].ptr, out["sums"].ptr, P(g_c), B, R, R, 1e-12, out["g_com"].ptr, None) == 0
+        torch.cuda.synchronize()
+        for k, o in out.items():
+            assert o.intact(), f"{k}: guard region overwritten (impl {impl})"
+            assert o.written(), f"{k}: output not fully written (impl {impl})"
