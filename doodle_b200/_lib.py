@@ -13,7 +13,7 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libhelio_sm100.so")
 CSRC = os.path.join(_HERE, "csrc")
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 SPLAT_AUTO, SPLAT_SIMT, SPLAT_TC = 0, 1, 2
 
@@ -23,7 +23,7 @@ EXPORTS = (
     "helio_profile_enable", "helio_profile_count", "helio_profile_get",
     "helio_distance_maps_workspace_bytes", "helio_distance_maps",
     "helio_com_fwd", "helio_com_bwd",
-    "helio_loss_bwd_packed", "helio_loss_pack", "helio_step_fwd", "helio_step_bwd",
+    "helio_loss_bwd_packed", "helio_loss_pack", "helio_step_partials_floats", "helio_step_fwd", "helio_step_bwd",
 )
 
 
@@ -101,7 +101,9 @@ def _declare(lib):
     lib.helio_loss_pack.restype = i
     lib.helio_loss_pack.argtypes = [p, i, p, p]
     lib.helio_step_fwd.restype = i
-    lib.helio_step_fwd.argtypes = [sp, p, p, p, p, p, i, i, i, i, i] + [p] * 14 + [p, i64, p]
+    lib.helio_step_fwd.argtypes = [sp, p, p, p, p, p, i, i, i, i, i] + [p] * 15 + [p, i64, p]
+    lib.helio_step_partials_floats.restype = i64
+    lib.helio_step_partials_floats.argtypes = [i, i, i, i]
     lib.helio_step_bwd.restype = i
     lib.helio_step_bwd.argtypes = [sp] + [p] * 9 + [i, i, i, i] + [p] * 7 + [p, p, p, p]
 

@@ -145,7 +145,16 @@ geom_fwd_kernel(Scene sc, const float* __restrict__ helio, const float* __restri
     float bnd = 0.f, ang = 0.f;
     if (idx < M) {
         const int b = (int)(idx / N), n = (int)(idx - (long long)b * N);
-        V3 h = ld3(helio + 3 * n), s = ld3(sun + 3 * b), a = ld3(action + 3 * idx);
+        V3 h = ld3(helio + 3 * n), s = ld3(sun + 3 * b), a;
+        if (action) {
+            a = ld3(action + 3 * idx);
+        } else {
+            // no action: aim with the ideal normal (the target render of HelioEnv.step, test_environment.py:429-433);
+            // same arithmetic as the ideal-normal output below, so it equals feeding that output back in
+            V3 inc = s - h;
+            float inn = fmaxf(norm(inc), 1e-9f);
+            a = ideal_normal(sc, h, v3(inc.x / inn, inc.y / inn, inc.z / inn));
+        }
         float e0 = 0.f, e1 = 0.f;
         if (errs) {
             float2 e = __ldg(reinterpret_cast<const float2*>(errs) + idx);

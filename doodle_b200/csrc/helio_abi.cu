@@ -147,7 +147,7 @@ HELIO_API int helio_geom_fwd(const helio_scene_t* scene, const float* helio_pos,
                    float* bounds, float* angles, float* sums, void* workspace, int64_t workspace_bytes, void* stream) {
     const DeviceInfo* d = nullptr;
     if (int rc = require_device(&d)) return rc;
-    HELIO_REQUIRE(scene && helio_pos && sun && action && params && actual && refl, "null pointer");
+    HELIO_REQUIRE(scene && helio_pos && sun && params && actual && refl, "null pointer");   // action may be NULL (ideal aim)
     HELIO_REQUIRE(B > 0 && N > 0, "B, N must be positive");
     if (sums) {
         HELIO_REQUIRE(workspace != nullptr, "sums requested without workspace");
@@ -177,27 +177,39 @@ HELIO_API int helio_geom_bwd(const helio_scene_t* scene, const float* helio_pos,
     return 0;
 }
 
-HELIO_API int helio_splat_fwd(const float* params, int B, int N, int R, float width, float height, float* img, int impl,
-                    void* stream) {
+namespace {
+bool splat_fwd_uses_tc(int impl, int B, int N, int R) {
+    const bool tc_ok = splat_tc_fwd_supported(B, N, R);
+    return (impl == HELIO_SPLAT_TC && tc_ok) || (impl == HELIO_SPLAT_AUTO && tc_ok && splat_tc_fwd_preferred(B, N, R));
+}
+
+int splat_fwd_impl(const float* params, int B, int N, int R, float width, float height, float* img, int impl, void* stream,
+                   int fuse, const FwdFuse& fz) {
     const DeviceInfo* d = nullptr;
     if (int rc = require_device(&d)) return rc;
     HELIO_REQUIRE(params && img, "null pointer");
     HELIO_REQUIRE(B > 0 && N > 0 && R > 0, "B, N, R must be positive");
     HELIO_REQUIRE(impl >= HELIO_SPLAT_AUTO && impl <= HELIO_SPLAT_TC, "unknown impl");
     KernelTimer timer("splat_fwd", stream);
-    const bool tc_ok = splat_tc_fwd_supported(B, N, R);
-    if (impl == HELIO_SPLAT_TC && !tc_ok)
+    if (impl == HELIO_SPLAT_TC && !splat_tc_fwd_supported(B, N, R))
         return set_error(HELIO_E_BADARG, "tcgen05 splat forward does not support this shape%s%s");
-    if (impl == HELIO_SPLAT_TC || (impl == HELIO_SPLAT_AUTO && tc_ok && splat_tc_fwd_preferred(B, N, R))) {
+    if (splat_fwd_uses_tc(impl, B, N, R)) {
         static const int split = []() {   // tuning / A-B switch: producer warps per operand slab (0 = auto)
             const char* e = std::getenv("HELIO_TC_FWD_SPLIT");
             return e ? std::atoi(e) : 0;
         }();
-        HELIO_CUDA_OK(splat_tc_fwd(params, img, B, N, R, width, height, d->sms, (cudaStream_t)stream, tc_pair_mode(), split));
+        HELIO_CUDA_OK(splat_tc_fwd(params, img, B, N, R, width, height, d->sms, (cudaStream_t)stream, tc_pair_mode(), split, fuse, fz));
     } else {
+        HELIO_REQUIRE(fuse == kFuseNone, "epilogue fusion needs the tcgen05 path");
         HELIO_CUDA_OK(splat_fwd_simt(params, img, B, N, R, width, height, d->sms, (cudaStream_t)stream));
     }
     return 0;
+}
+}  // namespace
+
+HELIO_API int helio_splat_fwd(const float* params, int B, int N, int R, float width, float height, float* img, int impl,
+                    void* stream) {
+    return splat_fwd_impl(params, B, N, R, width, height, img, impl, stream, kFuseNone, FwdFuse{});
 }
 
 HELIO_API int helio_splat_bwd(const float* params, const float* g_img, int B, int N, int R, float width, float height,
@@ -344,24 +356,60 @@ HELIO_API int helio_com_bwd(const float* img, const float* sums, const float* g_
     return 0;
 }
 
+HELIO_API int64_t helio_step_partials_floats(int B, int N, int R, int impl) {
+    const DeviceInfo* d = device_info();
+    if (!d || B <= 0 || N <= 0 || R <= 0 || !splat_fwd_uses_tc(impl, B, N, R)) return 0;
+    return (int64_t)B * splat_tc_fwd_partials_per_image(R, d->sms, tc_pair_mode()) * 3;
+}
+
 HELIO_API int helio_step_fwd(const helio_scene_t* scene, const float* helio_pos, const float* sun, const float* action,
                    const float* errs, const float* dmaps, int B, int N, int R, int impl, int render_target, float* params,
                    float* actual, float* refl, float* ideal, float* bounds, float* angles, float* img, float* target,
                    float* tx, float* per_img, float* packed, float* tgt_params, float* tgt_actual, float* tgt_refl,
-                   void* workspace, int64_t workspace_bytes, void* stream) {
-    HELIO_REQUIRE(scene && ideal && bounds && angles && img && target && tx && per_img && packed && dmaps, "null pointer");
+                   float* loss_partials, void* workspace, int64_t workspace_bytes, void* stream) {
+    HELIO_REQUIRE(scene && target && tx, "null pointer");
+    HELIO_REQUIRE(action == nullptr || (ideal && bounds && angles && img && per_img && packed && dmaps), "null pointer");
+    HELIO_REQUIRE(action != nullptr || render_target, "nothing to do");
     HELIO_REQUIRE(R > 0, "R must be positive");
-    // noisy field: K1 (with ideal normals, boundary, alignment and their sums -> packed[2..3]) + K2
+    const DeviceInfo* d = nullptr;
+    if (int rc = require_device(&d)) return rc;
+    // With the tensor-core splat the HBM-bound passes of the loss block ride in its epilogue (see FwdFuse): the
+    // target's per-image maximum, and the three per-image loss sums of the noisy image.
+    const bool tc = splat_fwd_uses_tc(impl, B, N, R);
+    const bool fused = loss_partials != nullptr && tc;   // loss sums in the noisy splat's epilogue
+    const char* fm = std::getenv("HELIO_FUSE_MAX");       // A/B switch (default on)
+    const bool fused_max = tc && !(fm && fm[0] == '0');  // target maximum in the target splat's epilogue
+    if (render_target) {
+        // error-free field aimed with the ideal normals (test_environment.py:429-436).  It depends on the suns only,
+        // so it goes first: a caller streaming the action in from the host overlaps that copy with these kernels.
+        HELIO_REQUIRE(tgt_params && tgt_actual && tgt_refl, "target render needs scratch buffers");
+        if (int rc = helio_geom_fwd(scene, helio_pos, sun, nullptr, nullptr, B, N, tgt_params, tgt_actual, tgt_refl, nullptr,
+                                    nullptr, nullptr, nullptr, nullptr, 0, stream)) return rc;
+        if (fused_max) {
+            HELIO_CUDA_OK(cudaMemsetAsync(tx, 0, (size_t)B * sizeof(float), (cudaStream_t)stream));
+            FwdFuse fz{};
+            fz.tile_max = tx;        // consumers clamp at 1e-6 (test_environment.py:436)
+            if (int rc = splat_fwd_impl(tgt_params, B, N, R, scene->width, scene->height, target, impl, stream, kFuseMax, fz)) return rc;
+        } else {
+            if (int rc = helio_splat_fwd(tgt_params, B, N, R, scene->width, scene->height, target, impl, stream)) return rc;
+            if (int rc = helio_image_max(target, B, R, tx, stream)) return rc;
+        }
+    }
+    if (action == nullptr) return 0;     // target-only call (phase 1 of a host-action step)
+    // noisy field: K1 (with ideal normals, boundary, alignment and their sums -> packed[2..3])
     if (int rc = helio_geom_fwd(scene, helio_pos, sun, action, errs, B, N, params, actual, refl, ideal, bounds, angles,
                                 packed + 2, workspace, workspace_bytes, stream)) return rc;
-    if (int rc = helio_splat_fwd(params, B, N, R, scene->width, scene->height, img, impl, stream)) return rc;
-    if (render_target) {
-        // error-free field aimed with the ideal normals (test_environment.py:429-436)
-        HELIO_REQUIRE(tgt_params && tgt_actual && tgt_refl, "target render needs scratch buffers");
-        if (int rc = helio_geom_fwd(scene, helio_pos, sun, ideal, nullptr, B, N, tgt_params, tgt_actual, tgt_refl, nullptr,
-                                    nullptr, nullptr, nullptr, nullptr, 0, stream)) return rc;
-        if (int rc = helio_splat_fwd(tgt_params, B, N, R, scene->width, scene->height, target, impl, stream)) return rc;
-        if (int rc = helio_image_max(target, B, R, tx, stream)) return rc;
+    if (!fused)
+        if (int rc = helio_splat_fwd(params, B, N, R, scene->width, scene->height, img, impl, stream)) return rc;
+    if (fused) {
+        FwdFuse fz{};
+        fz.target = target, fz.dmaps = dmaps, fz.tx = tx, fz.partials = loss_partials;
+        if (int rc = splat_fwd_impl(params, B, N, R, scene->width, scene->height, img, impl, stream, kFuseLoss, fz)) return rc;
+        KernelTimer timer("loss_pack", stream);
+        loss_pack_partials_kernel<<<1, kLossThreads, 0, (cudaStream_t)stream>>>(
+            loss_partials, splat_tc_fwd_partials_per_image(R, d->sms, tc_pair_mode()), B, per_img, packed);
+        HELIO_CUDA_OK(cudaGetLastError());
+        return 0;
     }
     if (int rc = helio_loss_fwd(img, target, dmaps, tx, B, R, per_img, stream)) return rc;
     return helio_loss_pack(per_img, B, packed, stream);

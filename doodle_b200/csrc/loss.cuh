@@ -90,7 +90,7 @@ loss_fwd_kernel(const float* __restrict__ img, const float* __restrict__ target,
                 const float* __restrict__ tx, int R, int slices, float* __restrict__ per_img) {
     const int b = blockIdx.x / slices, s = blockIdx.x % slices;
     const size_t npix = (size_t)R * R, off = (size_t)b * npix, stride = (size_t)slices * kLossThreads;
-    const float t = __ldg(tx + b);   // reference divides both images by tx
+    const float t = fmaxf(__ldg(tx + b), 1e-6f);   // reference divides both images by tx (clamped, test_environment.py:436)
     float acc[3] = {0.f, 0.f, 0.f};
     auto one = [&](float p, float q, float d) {
         const float diff = p / t - q / t;
@@ -181,6 +181,34 @@ __global__ void __launch_bounds__(kLossThreads) loss_pack_kernel(const float* __
     }
 }
 
+// Fused-epilogue variant: the forward splat left P partial records per image ({sum diff^2, sum |diff| dmaps,
+// sum |diff|} per epilogue warp); combine them in index order into per_img[b][3], then the batch sums as above.
+__global__ void __launch_bounds__(kLossThreads)
+loss_pack_partials_kernel(const float* __restrict__ partials, int P, int B, float* __restrict__ per_img, float* __restrict__ packed) {
+    double a0 = 0.0, a1 = 0.0;
+    for (int b = threadIdx.x; b < B; b += kLossThreads) {
+        const float* pp = partials + (size_t)b * P * 3;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+        for (int k = 0; k < P; ++k) s0 += __ldg(pp + 3 * k), s1 += __ldg(pp + 3 * k + 1), s2 += __ldg(pp + 3 * k + 2);
+        per_img[3 * b] = s0, per_img[3 * b + 1] = s1, per_img[3 * b + 2] = s2;
+        a0 += (double)s0;
+        a1 += (double)s1;
+    }
+    __shared__ double sh[2][kLossThreads / 32];
+    for (int o = 16; o > 0; o >>= 1) {
+        a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+        a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+    }
+    if ((threadIdx.x & 31) == 0) sh[0][threadIdx.x >> 5] = a0, sh[1][threadIdx.x >> 5] = a1;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s0 = 0.0, s1 = 0.0;
+        for (int w = 0; w < kLossThreads / 32; ++w) s0 += sh[0][w], s1 += sh[1][w];
+        packed[0] = (float)s0;
+        packed[1] = (float)s1;
+    }
+}
+
 // g_img = (2 g0 diff + (g1 dmaps + g2) sign(diff)) / tx (+ g_img_in); {g0,g1,g2} = g_per_img[b] (may be NULL) plus the
 // batch-wide {g_packed[0], g_packed[1], 0} (may be NULL): the adjoint of loss_pack_kernel folded in.
 __global__ void __launch_bounds__(kLossThreads)
@@ -189,7 +217,7 @@ loss_bwd_kernel(const float* __restrict__ img, const float* __restrict__ target,
                 const float* __restrict__ g_in, int R, int slices, float* __restrict__ g_img) {
     const int b = blockIdx.x / slices, s = blockIdx.x % slices;
     const size_t npix = (size_t)R * R, off = (size_t)b * npix;
-    const float t = __ldg(tx + b);
+    const float t = fmaxf(__ldg(tx + b), 1e-6f);
     float g0 = 0.f, g1 = 0.f, g2 = 0.f;
     if (g_per_img) g0 = __ldg(g_per_img + 3 * b), g1 = __ldg(g_per_img + 3 * b + 1), g2 = __ldg(g_per_img + 3 * b + 2);
     if (g_packed) g0 += __ldg(g_packed), g1 += __ldg(g_packed + 1);

@@ -207,14 +207,30 @@ struct SplatTcCtx {
 template <int NT, int CG, int PS>
 using SplatFwdTc = SplatTcLayout<NT, CG, NT / CG, PS, PS>;
 
+// Work fused into the forward epilogue while the accumulator row sits in registers (the kernel is tensor-bound and
+// leaves HBM almost idle, so the HBM-bound passes of the loss block ride along for free):
+//   kFuseMax : tile_max[b] = max over the image (atomicMax on the int pattern: values are >= 0, order-free), which
+//              replaces image_max_kernel for the target render;
+//   kFuseLoss: per-warp partials {sum diff^2, sum |diff| dmaps, sum |diff|}, diff = img/t - target/t, written to
+//              partials[b][tile][cta][warp][3] and combined in index order by loss_pack_partials_kernel, which
+//              replaces loss_fwd_kernel's pass over the image.
+enum : int { kFuseNone = 0, kFuseMax = 1, kFuseLoss = 2 };
+struct FwdFuse {
+    float* tile_max;         // [B]           kFuseMax (zero-initialised by the caller)
+    const float* target;     // [B][R][R]     kFuseLoss
+    const float* dmaps;      // [B][R][R]
+    const float* tx;         // [B]           (clamped to 1e-6 here)
+    float* partials;         // [B][tiles][CG][4][3]
+};
+
 // Producer mapping: a warp owns 32 operand rows (image rows for A, image columns for B); a lane owns
 // 4 consecutive heliostats of the stage (one 16-byte chunk of the K-major row) and walks 8 of the
 // rows, so the footprint parameters sit in registers (loaded once per stage, prefetched one stage
 // ahead) and every warp store writes four full 128-byte rows of the swizzled tile, conflict-free.
-template <int NT, int CG, int PS>
+template <int NT, int CG, int PS, int FUSE>
 __global__ void __launch_bounds__(SplatFwdTc<NT, CG, PS>::kThreads, 1)
 splat_fwd_tc_kernel(const float4* __restrict__ params, float* __restrict__ img, int N, int R, Axis ax, Axis ay,
-                    int tiles_i, int tiles_j, int num_tiles) {
+                    int tiles_i, int tiles_j, int num_tiles, FwdFuse fz) {
     using C = SplatFwdTc<NT, CG, PS>;
     extern __shared__ uint8_t smem_raw[];
     SplatTcCtx<C, CG> cx;
@@ -324,19 +340,24 @@ splat_fwd_tc_kernel(const float4* __restrict__ params, float* __restrict__ img, 
             const int b = tile / tiles_per_img, t = tile % tiles_per_img;
             const int i0 = (t / tiles_j) * kTileM + (int)cx.rank * C::kM, j0 = (t % tiles_j) * NT;
             const int acc = tcount & 1;
+            float tinv_t = 1.f;                      // kFuseLoss: the image's normaliser, fetched before the wait
+            if constexpr (FUSE == kFuseLoss) tinv_t = fmaxf(__ldg(fz.tx + b), 1e-6f);
             tc::mbar_wait_sleep(&cx.tfull[acc], (tcount >> 1) & 1);
             tc::tc_fence_after();
             const int i = i0 + q * 32 + lane;
-            float* dst = img + ((size_t)b * R + i) * R + j0;
+            const size_t row_off = ((size_t)b * R + i) * R + j0;
+            float* dst = img + row_off;
             const uint32_t taddr = cx.tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * NT);
             const bool vec = (R & 3) == 0;
+            float f0 = 0.f, f1 = 0.f, f2 = 0.f;      // kFuseMax: f0 = running max; kFuseLoss: the three sums
 #pragma unroll 1
             for (int cb = 0; cb < NT; cb += 32) {
                 if (j0 + cb >= R) break;
                 float v[32];
                 tc::tmem_ld_32x32(taddr + cb, v);
                 if (i < R) {
-                    if (vec && j0 + cb + 32 <= R) {
+                    const bool full = vec && j0 + cb + 32 <= R;
+                    if (full) {
 #pragma unroll
                         for (int e = 0; e < 32; e += 4)
                             *reinterpret_cast<float4*>(dst + cb + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
@@ -345,9 +366,48 @@ splat_fwd_tc_kernel(const float4* __restrict__ params, float* __restrict__ img, 
                         for (int e = 0; e < 32; ++e)
                             if (j0 + cb + e < R) dst[cb + e] = v[e];
                     }
+                    if constexpr (FUSE == kFuseMax) {
+#pragma unroll
+                        for (int e = 0; e < 32; ++e)
+                            if (full || j0 + cb + e < R) f0 = fmaxf(f0, v[e]);
+                    }
+                    if constexpr (FUSE == kFuseLoss) {
+                        const float* tg = fz.target + row_off + cb;
+                        const float* dm = fz.dmaps + row_off + cb;
+                        auto one = [&](float p, float qv, float d) {
+                            const float diff = p / tinv_t - qv / tinv_t;      // same arithmetic as loss_fwd_kernel
+                            const float ae = fabsf(diff);
+                            f0 = fmaf(diff, diff, f0);
+                            f1 = fmaf(ae, d, f1);
+                            f2 += ae;
+                        };
+                        if (full) {
+#pragma unroll
+                            for (int e = 0; e < 32; e += 4) {
+                                const float4 tq = __ldg(reinterpret_cast<const float4*>(tg + e));
+                                const float4 dq = __ldg(reinterpret_cast<const float4*>(dm + e));
+                                one(v[e], tq.x, dq.x), one(v[e + 1], tq.y, dq.y), one(v[e + 2], tq.z, dq.z), one(v[e + 3], tq.w, dq.w);
+                            }
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 32; ++e)
+                                if (j0 + cb + e < R) one(v[e], __ldg(tg + e), __ldg(dm + e));
+                        }
+                    }
                 }
             }
             cx.epilogue_release(acc);
+            if constexpr (FUSE == kFuseMax) {
+                f0 = warp_max(f0);
+                if (lane == 0) atomicMax(reinterpret_cast<int*>(fz.tile_max + b), __float_as_int(f0));
+            }
+            if constexpr (FUSE == kFuseLoss) {
+                f0 = warp_sum(f0), f1 = warp_sum(f1), f2 = warp_sum(f2);
+                if (lane == 0) {
+                    float* pp = fz.partials + ((((size_t)b * tiles_per_img + t) * CG + cx.rank) * 4 + q) * 3;
+                    pp[0] = f0, pp[1] = f1, pp[2] = f2;
+                }
+            }
         }
     }
     cx.teardown();
@@ -383,37 +443,46 @@ inline cudaError_t launch_tc_groups(Kernel kernel, long long num_tiles, int num_
     return cudaLaunchKernelEx(&cfg, kernel, args...);
 }
 
+// tiles per image and partial records per image of the shape the forward picks for R (for the fused-loss buffers)
+inline int splat_tc_fwd_cg(int R, int num_sms, int pair) { return (R > 128 && pair != 1 && num_sms >= 2) ? 2 : 1; }
+inline int splat_tc_fwd_partials_per_image(int R, int num_sms, int pair) {
+    const int cg = splat_tc_fwd_cg(R, num_sms, pair);
+    const int nt = R > 128 ? 256 : (R > 64 ? 128 : 64);
+    const int tiles = ((R + 128 * cg - 1) / (128 * cg)) * ((R + nt - 1) / nt);
+    return tiles * cg * 4;
+}
+
 template <int NT, int CG, int PS>
 inline cudaError_t launch_splat_fwd_tc(const float* params, float* img, int B, int N, int R, float width, float height,
-                                       int num_sms, cudaStream_t st) {
+                                       int num_sms, cudaStream_t st, int fuse, const FwdFuse& fz) {
     using C = SplatFwdTc<NT, CG, PS>;
     const int tiles_i = (R + C::kM * CG - 1) / (C::kM * CG), tiles_j = (R + NT - 1) / NT;
     const long long num_tiles = (long long)B * tiles_i * tiles_j;
     if (num_tiles > 0x7fffffffLL) return cudaErrorInvalidValue;
-    return launch_tc_groups<CG>(splat_fwd_tc_kernel<NT, CG, PS>, num_tiles, num_sms, C::kThreads, C::kSmemBytes, st,
-                                reinterpret_cast<const float4*>(params), img, N, R, make_axis(width, R), make_axis(height, R),
-                                tiles_i, tiles_j, (int)num_tiles);
+    auto go = [&](auto kernel) {
+        return launch_tc_groups<CG>(kernel, num_tiles, num_sms, C::kThreads, C::kSmemBytes, st,
+                                    reinterpret_cast<const float4*>(params), img, N, R, make_axis(width, R), make_axis(height, R),
+                                    tiles_i, tiles_j, (int)num_tiles, fz);
+    };
+    if (fuse == kFuseMax) return go(splat_fwd_tc_kernel<NT, CG, PS, kFuseMax>);
+    if (fuse == kFuseLoss) return go(splat_fwd_tc_kernel<NT, CG, PS, kFuseLoss>);
+    return go(splat_fwd_tc_kernel<NT, CG, PS, kFuseNone>);
 }
 
 // pair = 0: auto (CTA pairs for images taller than 128 rows), 1: single CTA, 2: CTA pairs
 // split = producer warps per 32-row operand slab (1 or 2; 0 = auto)
 inline cudaError_t splat_tc_fwd(const float* params, float* img, int B, int N, int R, float width, float height, int num_sms,
-                                cudaStream_t st, int pair = 0, int split = 0) {
+                                cudaStream_t st, int pair = 0, int split = 0, int fuse = kFuseNone, const FwdFuse& fz = FwdFuse{}) {
+#define HELIO_FWD(NT_, CG_, PS_) launch_splat_fwd_tc<NT_, CG_, PS_>(params, img, B, N, R, width, height, num_sms, st, fuse, fz)
     if (R > 128) {
-        if (pair != 1 && num_sms >= 2) {
-            if (split == 2) return launch_splat_fwd_tc<256, 2, 2>(params, img, B, N, R, width, height, num_sms, st);
-            return launch_splat_fwd_tc<256, 2, 1>(params, img, B, N, R, width, height, num_sms, st);
-        }
-        return launch_splat_fwd_tc<256, 1, 1>(params, img, B, N, R, width, height, num_sms, st);
+        if (splat_tc_fwd_cg(R, num_sms, pair) == 2) return split == 2 ? HELIO_FWD(256, 2, 2) : HELIO_FWD(256, 2, 1);
+        return HELIO_FWD(256, 1, 1);
     }
-    if (R > 64) {
-        if (split == 2) return launch_splat_fwd_tc<128, 1, 2>(params, img, B, N, R, width, height, num_sms, st);
-        return launch_splat_fwd_tc<128, 1, 1>(params, img, B, N, R, width, height, num_sms, st);
-    }
+    if (R > 64) return split == 2 ? HELIO_FWD(128, 1, 2) : HELIO_FWD(128, 1, 1);
     // measured on B200: two producer warps per slab only pay off for the 64-wide tile (-11 % at N = 5000; the wider
     // tiles are bound by shared-memory bandwidth, not producer latency, and lose 8-10 %)
-    if (split == 1) return launch_splat_fwd_tc<64, 1, 1>(params, img, B, N, R, width, height, num_sms, st);
-    return launch_splat_fwd_tc<64, 1, 2>(params, img, B, N, R, width, height, num_sms, st);
+    return split == 1 ? HELIO_FWD(64, 1, 1) : HELIO_FWD(64, 1, 2);
+#undef HELIO_FWD
 }
 
 // ================================================================================================

@@ -236,9 +236,8 @@ class HelioEnv(_EnvBase):
         self._target_cache = None
         self.ref_field.init_actions(self.sun_pos)
         with torch.no_grad():
-            out = self.ref_field._render_full(self.sun_pos, self.ref_field.initial_action, want_aux=True)
-            timg = out.img
-        self._ideal_of_suns = out.ideal          # K1's ideal normals: a function of the suns only (host-action path)
+            ideal_normals = self.ref_field.calculate_ideal_normals(self.sun_pos)
+            timg, _ = self.ref_field.render(self.sun_pos, self.ref_field.initial_action, ideal_normals)
         self.distance_maps = make_distance_maps(timg, impl=self.distance_maps_impl)
         self.ref_min = torch.min(timg)
         self.ref_max = torch.max(timg)
@@ -297,7 +296,7 @@ class HelioEnv(_EnvBase):
             img, packed, _actual, refl, ideal_normals, bounds, angles, per_img, target, tx, action_dev = HostStepFn.apply(
                 act.contiguous(), self.sun_pos, _cf(nf._select_errors(B)), nf.heliostat_positions, self.distance_maps, nf.scene(),
                 nf._geom_workspace(B), R, nf.splat_impl, nf.splat_impl if nf.splat_impl_bwd is None else nf.splat_impl_bwd,
-                cached[0], cached[1], self._ideal_of_suns, self._copy_stream, self.host_chunks)
+                cached[0], cached[1], self._copy_stream, self.host_chunks)
             if self.cache_target and self._target_cache is None:
                 self._target_cache = (target, tx)
             out = SimpleNamespace(refl=refl, bounds=bounds, angles=angles)

@@ -15,6 +15,7 @@ SplatFn.backward hands the per-(b,n) moments {S0,Sx,Sy,S2} of g*G to GeomFn.back
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional
 
 import torch
@@ -231,6 +232,35 @@ class ImageLossFn(torch.autograd.Function):
         return g_img, None, None, None
 
 
+_PARTIALS_FLOATS = {}
+
+
+FUSE_LOSS_EPILOGUE = os.environ.get("HELIO_FUSE_LOSS", "0") == "1"
+
+
+def _loss_partials(lib, B, N, R, impl, dev):
+    """(scratch for the loss sums accumulated in the splat epilogue or None = separate loss_fwd pass, shape takes the
+    tcgen05 splat).
+
+    The loss fusion is off by default: measured on B200 the fused epilogue's per-row loads of target / dmaps add ~20 %
+    to the L1 data-pipe wavefronts that bound the forward splat (+0.8 ms at N=2000, R=256, B=4096) and save only the
+    0.48 ms loss pass.  The per-image maximum of the target (no extra loads) is always fused on the tcgen05 path."""
+    key = (B, N, R, impl)
+    n = _PARTIALS_FLOATS.get(key)
+    if n is None:
+        n = _PARTIALS_FLOATS[key] = int(lib.helio_step_partials_floats(B, N, R, impl))
+    if not FUSE_LOSS_EPILOGUE or n == 0:
+        return None, n > 0
+    return torch.empty(n, dtype=torch.float32, device=dev), True
+
+
+def _step_fwd_kernels(render_target: bool, fused: bool, tc: bool = True) -> int:
+    """Kernels helio_step_fwd enqueues: K1, K2, loss_pack (+ loss_fwd when the loss is not fused into K2's epilogue)
+    and, with the target render, K1, K2 (+ image_max on the CUDA-core path; the tcgen05 splat folds the maximum into
+    its epilogue; the memset is not counted)."""
+    return (3 if fused else 4) + ((2 if tc else 3) if render_target else 0)
+
+
 class StepFn(torch.autograd.Function):
     """Whole HelioEnv.step forward / backward as ONE C-ABI call each (helio_step_fwd / helio_step_bwd).
 
@@ -260,17 +290,18 @@ class StepFn(torch.autograd.Function):
         if render_target:
             target, tx = torch.empty(B, R, R, **f32), torch.empty(B, **f32)
             scratch = torch.empty(B * N * 10, **f32)     # params, actual, refl of the target render (discarded)
+        partials, tc = _loss_partials(lib, B, N, R, impl, dev)
         with _Call("step_fwd", dev):
             rc = lib.helio_step_fwd(
                 C.byref(scene), _ptr(helio), _ptr(sun), _ptr(action), _ptr(errs), _ptr(dmaps), B, N, R, impl,
                 1 if render_target else 0, _ptr(params), _ptr(actual), _ptr(refl), _ptr(ideal), _ptr(bounds), _ptr(angles),
                 _ptr(img), _ptr(target), _ptr(tx), _ptr(per_img), _ptr(packed),
                 _ptr(scratch), _ptr(scratch[4 * B * N:]) if render_target else None,
-                _ptr(scratch[7 * B * N:]) if render_target else None,
+                _ptr(scratch[7 * B * N:]) if render_target else None, _ptr(partials),
                 _ptr(workspace), workspace.numel() * workspace.element_size(), _stream())
         _lib.check(rc, "helio_step_fwd")
         global _LAUNCHES
-        _LAUNCHES += 6 if render_target else 3       # 7 / 4 kernels enqueued by the call, minus the one _Call counted
+        _LAUNCHES += _step_fwd_kernels(render_target, partials is not None, tc) - 1      # _Call counted one
         ctx.save_for_backward(action, sun, errs, helio, dmaps, params, img, target, tx)
         ctx.cfg = (scene, R, impl_bwd)
         ctx.set_materialize_grads(False)
@@ -313,7 +344,7 @@ class HostStepFn(torch.autograd.Function):
     batch in the forward)."""
 
     @staticmethod
-    def forward(ctx, action_host, sun, errs, helio, dmaps, scene, workspace, R, impl, impl_bwd, target, tx, ideal, copy_stream,
+    def forward(ctx, action_host, sun, errs, helio, dmaps, scene, workspace, R, impl, impl_bwd, target, tx, copy_stream,
                 chunks: int):
         lib = _lib.load()
         B, N = sun.shape[0], helio.shape[0]
@@ -332,24 +363,25 @@ class HostStepFn(torch.autograd.Function):
         img = torch.empty(B, R, R, **f32)
         per_img, packed = torch.empty(B, 3, **f32), torch.empty(4, **f32)
         global _LAUNCHES
+        partials, tc = _loss_partials(lib, B, N, R, impl, dev)
+        render_target = target is None
+        nws = workspace.numel() * workspace.element_size()
         with _Call("step_fwd_host", dev):
-            if target is None:                           # target render first: it does not need the action
+            if render_target:                            # phase 1, target only: it does not need the action
                 target, tx = torch.empty(B, R, R, **f32), torch.empty(B, **f32)
                 scratch = torch.empty(B * N * 10, **f32)
-                rc = lib.helio_geom_fwd(C.byref(scene), _ptr(helio), _ptr(sun), _ptr(ideal), None, B, N, _ptr(scratch),
-                                        _ptr(scratch[4 * B * N:]), _ptr(scratch[7 * B * N:]), None, None, None, None, None, 0, _stream())
-                _lib.check(rc, "helio_geom_fwd")
-                _lib.check(lib.helio_splat_fwd(_ptr(scratch), B, N, R, scene.width, scene.height, _ptr(target), impl, _stream()), "helio_splat_fwd")
-                _lib.check(lib.helio_image_max(_ptr(target), B, R, _ptr(tx), _stream()), "helio_image_max")
-                _LAUNCHES += 3
+                rc = lib.helio_step_fwd(
+                    C.byref(scene), _ptr(helio), _ptr(sun), None, None, None, B, N, R, impl, 1, None, None, None, None, None, None,
+                    None, _ptr(target), _ptr(tx), None, None, _ptr(scratch), _ptr(scratch[4 * B * N:]), _ptr(scratch[7 * B * N:]),
+                    _ptr(partials), _ptr(workspace), nws, _stream())
+                _lib.check(rc, "helio_step_fwd (target)")
             main.wait_event(landed)
             rc = lib.helio_step_fwd(
                 C.byref(scene), _ptr(helio), _ptr(sun), _ptr(action), _ptr(errs), _ptr(dmaps), B, N, R, impl, 0,
                 _ptr(params), _ptr(actual), _ptr(refl), _ptr(ideal_out), _ptr(bounds), _ptr(angles), _ptr(img), _ptr(target),
-                _ptr(tx), _ptr(per_img), _ptr(packed), None, None, None,
-                _ptr(workspace), workspace.numel() * workspace.element_size(), _stream())
+                _ptr(tx), _ptr(per_img), _ptr(packed), None, None, None, _ptr(partials), _ptr(workspace), nws, _stream())
         _lib.check(rc, "helio_step_fwd")
-        _LAUNCHES += 3
+        _LAUNCHES += _step_fwd_kernels(render_target, partials is not None, tc) - 1
         ctx.save_for_backward(action, sun, errs, helio, dmaps, params, img, target, tx)
         ctx.cfg = (scene, R, impl_bwd, copy_stream, max(1, min(int(chunks), B)), action_host.shape, action_host.is_pinned())
         ctx.set_materialize_grads(False)
@@ -394,4 +426,4 @@ class HostStepFn(torch.autograd.Function):
                     h_grad.narrow(0, b0, nb).copy_(g_action.narrow(0, b0, nb), non_blocking=True)
         main.wait_stream(copy_stream)                 # g_action is freed on main: keep the allocator's ordering
         copy_stream.synchronize()                     # the caller owns a host tensor: it must be complete
-        return (h_grad.view(host_shape),) + (None,) * 14
+        return (h_grad.view(host_shape),) + (None,) * 13

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define HELIO_ABI_VERSION 2
+#define HELIO_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define HELIO_API __attribute__((visibility("default")))
@@ -94,7 +94,8 @@ HELIO_API int64_t helio_geom_workspace_bytes(int B, int N);
  *   calculate_ideal_normals         :256-278          (ideal, optional)
  *   boundary(return_all=True)       test_environment.py:101-130   (bounds, optional)
  *   calculate_angles_mrad           test_environment.py:132-155   (angles, optional)
- * in : helio[N][3], sun[B][3], action[B][N][3], errs[B][N][2] in mrad (NULL = zero errors)
+ * in : helio[N][3], sun[B][3], action[B][N][3] (NULL = aim every mirror with its ideal normal, the
+ *      target render of test_environment.py:429-433), errs[B][N][2] in mrad (NULL = zero errors)
  * out: params[B][N][4] = {a, b, k2, amp}: the heliostat's footprint on the receiver is
  *        amp * exp2(-k2 (x_i - a)^2) * exp2(-k2 (y_j - b)^2)   (k2 = log2(e)/max(2 sigma^2,1e-12);
  *        an invalid ray has k2 = 0, amp = 1: +1 on every pixel, :141-143)
@@ -187,14 +188,24 @@ HELIO_API int helio_loss_pack(const float* per_img, int B, float* packed, void* 
  * The caller divides packed by {B R^2, B, B N, B N} (after an all-reduce when B is sharded).
  * render_target == 0 reuses the caller's target / tx (they depend on sun only).
  * tgt_params[B][N][4], tgt_actual/tgt_refl[B][N][3] are scratch for the target render (may be NULL
- * when render_target == 0).  `workspace` as for helio_geom_fwd.  Same launches, same results as
- * calling the individual entry points; it exists to cut host overhead for small fields. */
+ * when render_target == 0).  `workspace` as for helio_geom_fwd.  Same results as calling the individual
+ * entry points (to summation order); it exists to cut host overhead for small fields and to fuse the
+ * loss passes into the splat epilogues for large ones.
+ *
+ * The target render is enqueued first (it depends on the suns only); action == NULL stops after it
+ * (phase 1 of a step whose action is still being copied in from the host).
+ *
+ * loss_partials (may be NULL): helio_step_partials_floats(B, N, R, impl) floats of scratch.  When given and
+ * the shape takes the tcgen05 splat, image_max and loss_fwd do not run as separate passes: the target's
+ * per-image maximum and the three per-image loss sums are accumulated in the splat epilogues while the
+ * image rows are in registers (tx then holds the UNclamped maximum; every consumer clamps at 1e-6). */
+HELIO_API int64_t helio_step_partials_floats(int B, int N, int R, int impl);
 HELIO_API int helio_step_fwd(const helio_scene_t* scene_host, const float* helio, const float* sun,
                    const float* action, const float* errs, const float* dmaps,
                    int B, int N, int R, int impl, int render_target,
                    float* params, float* actual, float* refl, float* ideal, float* bounds, float* angles,
                    float* img, float* target, float* tx, float* per_img, float* packed,
-                   float* tgt_params, float* tgt_actual, float* tgt_refl,
+                   float* tgt_params, float* tgt_actual, float* tgt_refl, float* loss_partials,
                    void* workspace, int64_t workspace_bytes, void* stream);
 
 /* Backward of helio_step_fwd down to g_action[B][N][3]: K4' (g_img) -> K3 (moments) -> K1'.

@@ -276,6 +276,33 @@ def test_center_of_mass_matches_oracle(B, H, W):
     assert rel_err(gr.cpu().numpy().reshape(-1), g64.reshape(-1)) < 1e-5
 
 
+@pytest.mark.parametrize("N,R,B", [(60, 128, 3), (70, 256, 2), (33, 100, 3), (40, 512, 2), (90, 64, 4)])
+def test_fused_epilogues_equal_separate_loss_passes(N, R, B):
+    """At shapes that take the tcgen05 splat, helio_step_fwd folds image_max and loss_fwd into the splat epilogues.
+    Images must be bit-equal to the composed route; metrics, mae_image and gradients equal to summation-order rounding."""
+    from doodle_b200 import HelioEnv, functional as Fn
+    res = []
+    for fused in (True, False):
+        Fn.FUSE_LOSS_EPILOGUE = fused                          # opt-in (HELIO_FUSE_LOSS=1); the max fusion is always on
+        torch.manual_seed(17)
+        helio = torch.rand(N, 3, device=_dev()) * 10 + 80
+        helio[:, 2] = 0
+        env = HelioEnv(helio, torch.tensor([0., -5., 0.], device=_dev()), (15., 15.), torch.tensor([0., 1., 0.], device=_dev()),
+                       sigma_scale=0.03, error_scale_mrad=60.0, resolution=R, batch_size=B, device="cuda:0", fused_step=fused)
+        env.reset()
+        a = (env.ideal_normals + 0.01 * torch.randn_like(env.ideal_normals)).flatten(1).requires_grad_(True)
+        obs, m, mon = env.step(a)
+        g, = torch.autograd.grad(m["mse"] + 0.01 * m["dist"] + m["bound"] + m["alignment_loss"], a)
+        res.append((obs, m, mon, g))
+    Fn.FUSE_LOSS_EPILOGUE = False
+    (o1, m1, mon1, g1), (o2, m2, mon2, g2) = res
+    assert torch.equal(o1["img"], o2["img"])
+    for k in m1:
+        np.testing.assert_allclose(float(m1[k].detach()), float(m2[k].detach()), rtol=3e-6, err_msg=k)
+    np.testing.assert_allclose(mon1["mae_image"].detach().cpu().numpy(), mon2["mae_image"].detach().cpu().numpy(), rtol=3e-6)
+    assert rel_err(g1.cpu().numpy(), g2.cpu().numpy()) < 3e-6
+
+
 def test_env_reset_matches_reference():
     g = load_golden("env_readme")
     env = _env_from_golden(g)
@@ -558,12 +585,18 @@ def test_kernels_stay_inside_their_buffers(N, R, B):
     out = {k: Guarded(n) for k, n in dict(params=4 * BN, actual=3 * BN, refl=3 * BN, ideal=3 * BN, bounds=BN, angles=BN, img=BRR,
                                           target=BRR, tx=B, per_img=3 * B, packed=4, tparams=4 * BN, tactual=3 * BN, trefl=3 * BN,
                                           g_img=BRR, moments=4 * BN, g_action=3 * BN, edt=BRR, coords=2 * B, sums=3 * B, g_com=BRR).items()}
-    for impl in (2, 1):                                        # tcgen05 and CUDA-core splats
+    for impl, fuse in ((2, True), (2, False), (1, False)):     # tcgen05 (fused / separate loss passes) and CUDA-core splats
         for o in out.values():
             o.view.fill_(float("nan"))
+        npart = int(lib.helio_step_partials_floats(B, N, R, impl)) if fuse else 0
+        assert (npart > 0) == fuse
+        out["partials"] = Guarded(max(npart, 1))
+        if not fuse:
+            out["partials"].view.fill_(0.0)
         rc = lib.helio_step_fwd(C.byref(sc), P(helio), P(sun), P(action), P(errs), P(dmaps), B, N, R, impl, 1,
                                 *[out[k].ptr for k in ("params", "actual", "refl", "ideal", "bounds", "angles", "img", "target", "tx",
-                                                       "per_img", "packed", "tparams", "tactual", "trefl")], P(ws), ws_bytes, None)
+                                                       "per_img", "packed", "tparams", "tactual", "trefl")],
+                                out["partials"].ptr if fuse else None, P(ws), ws_bytes, None)
         assert rc == 0, lib.helio_last_error()
         g_packed = torch.tensor([1.0, 0.01, 1.0, 1.0], device=dev)
         rc = lib.helio_step_bwd(C.byref(sc), P(helio), P(sun), P(action), P(errs), out["params"].ptr, out["img"].ptr, out["target"].ptr,
@@ -578,5 +611,5 @@ def test_kernels_stay_inside_their_buffers(N, R, B):
         assert lib.helio_com_bwd(out["img"].ptr, out["sums"].ptr, P(g_c), B, R, R, 1e-12, out["g_com"].ptr, None) == 0
         torch.cuda.synchronize()
         for k, o in out.items():
-            assert o.intact(), f"{k}: guard region overwritten (impl {impl})"
-            assert o.written(), f"{k}: output not fully written (impl {impl})"
+            assert o.intact(), f"{k}: guard region overwritten (impl {impl}, fused {fuse})"
+            assert o.written(), f"{k}: output not fully written (impl {impl}, fused {fuse})"
