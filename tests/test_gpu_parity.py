@@ -613,3 +613,19 @@ def test_kernels_stay_inside_their_buffers(N, R, B):
         for k, o in out.items():
             assert o.intact(), f"{k}: guard region overwritten (impl {impl}, fused {fuse})"
             assert o.written(), f"{k}: output not fully written (impl {impl}, fused {fuse})"
+
+
+def test_policy_trains_through_the_env():
+    """A small policy network trained on alignment_loss through HelioEnv.step (the data flow of the reference trainer's
+    rollout, train_with_env.py:171-216): the hand-written backward must drive the loss down."""
+    import importlib.util, os, sys
+    spec = importlib.util.spec_from_file_location("train_policy_c3", os.path.join(os.path.dirname(__file__), "..", "examples", "train_policy_c3.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    argv = sys.argv
+    sys.argv = ["train_policy_c3.py", "--iters", "40", "--B", "32", "--N", "12", "--R", "64", "--T", "2", "--k", "2", "--lr", "1e-3"]
+    try:
+        out = mod.main()
+    finally:
+        sys.argv = argv
+    assert out["alignment_loss_last"] < 0.7 * out["alignment_loss_first"], out
