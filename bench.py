@@ -113,26 +113,34 @@ def cpu_step_factory(N, R, n_suns, threads):
 
 
 def run_cpu_sample(N, R, budget_s, steps=1, warmup=0):
-    """Time the oracle port on a bounded sample; returns dict for `cpu_baseline`."""
+    """Time the oracle port on a bounded sample of the workload; returns (dict for `cpu_baseline`, seconds per step).
+
+    The port parallelises over suns, so the sample is one sun per host thread (more when the budget allows) over the
+    first N_s heliostats of the field, N_s sized so that (steps + warmup) steps fit `budget_s`.  The dense algorithm is
+    linear in the heliostat count, so evals/s of the sample is the rate of the full workload."""
     threads = os.cpu_count() or 1
-    # calibrate on one sun per thread-group of 1 to pick the sample size
+    n_cal = min(N, 64)
+    cal = cpu_step_factory(n_cal, R, 1, 1)
+    cal()                                            # first call pays imports / page faults
     t0 = time.perf_counter()
-    cpu_step_factory(N, R, 1, 1)()
-    t_one = time.perf_counter() - t0
-    per_step_budget = max(budget_s / max(steps + warmup, 1), t_one)
-    n_suns = int(max(1, min(threads * 4, threads * per_step_budget / max(t_one, 1e-6))))
-    n_suns = max(1, min(n_suns, 4 * threads))
-    step = cpu_step_factory(N, R, n_suns, threads)
+    cal()
+    t_unit = (time.perf_counter() - t0) / n_cal      # seconds per (sun, heliostat) on one thread
+    per_step_budget = budget_s / max(steps + warmup, 1)
+    n_s = int(min(N, max(32, per_step_budget / max(t_unit, 1e-9))))
+    n_suns = threads
+    if n_s == N:
+        n_suns = threads * int(max(1, min(4, per_step_budget / max(t_unit * N, 1e-9))))
+    step = cpu_step_factory(n_s, R, n_suns, threads)
     for _ in range(warmup):
         step()
     t0 = time.perf_counter()
     for _ in range(max(steps, 1)):
         step()
     dt = (time.perf_counter() - t0) / max(steps, 1)
-    evals = float(n_suns) * N * R * R
+    evals = float(n_suns) * n_s * R * R
     return dict(value=evals / dt, unit=UNIT, cores=threads, kind="port",
                 sample=f"oracle/helio_oracle.env_step (numpy port of the reference's dense algorithm, fp32): "
-                       f"{n_suns} suns x N={N} x R={R}, step fwd+target+losses+bwd, {dt:.2f} s/step on {threads} threads"), dt
+                       f"{n_suns} suns x {n_s} of N={N} heliostats x R={R}, step fwd+target+losses+bwd, {dt:.2f} s/step on {threads} threads"), dt
 
 
 def main_reference(args):
