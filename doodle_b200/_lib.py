@@ -11,7 +11,7 @@ import subprocess
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libhelio_sm100.so")
+LIB_PATH = os.environ.get("HELIO_LIB_PATH") or os.path.join(_HERE, "libhelio_sm100.so")   # override: experiments only
 CSRC = os.path.join(_HERE, "csrc")
 ABI_VERSION = 3
 
