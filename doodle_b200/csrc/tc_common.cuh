@@ -197,5 +197,33 @@ __device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
     lo = v - hi;
 }
 
+// ---- packed fp32x2 arithmetic (sm_100: FADD2 / FMUL2 / FFMA2, two IEEE results per instruction) ------------
+struct f32x2 {
+    unsigned long long r;
+};
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+    f32x2 p;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(p.r) : "f"(lo), "f"(hi));
+    return p;
+}
+__device__ __forceinline__ void unpack2(f32x2 p, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(p.r));
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+    f32x2 c;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(c.r) : "l"(a.r), "l"(b.r));
+    return c;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+    f32x2 c;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(c.r) : "l"(a.r), "l"(b.r));
+    return c;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d.r) : "l"(a.r), "l"(b.r), "l"(c.r));
+    return d;
+}
+
 }  // namespace tc
 }  // namespace helio
