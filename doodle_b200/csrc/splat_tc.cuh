@@ -254,19 +254,20 @@ splat_fwd_tc_kernel(const float4* __restrict__ params, float* __restrict__ img, 
 
     if (warp < C::kMmaWarp) {
         // ================= producers =================
-        // PS warps share a 32-row slab and each takes 32 / PS heliostats of a stage (PS = 2 halves the latency of a
-        // producer warp per stage, which is what bounds narrow tiles).  lane = (row subgroup rs, K chunk ch): per step
-        // a warp covers kRS rows x 32 / PS heliostats, each lane evaluating its 4 heliostats for one row and storing
-        // them as one 16-byte chunk of the swizzled row.
+        // A warp owns 32 / PS operand rows and all 32 heliostats of a stage (PS = 2: twice the producer warps, each
+        // with half the rows; a K split instead would halve the bytes per row a store instruction covers and double
+        // the shared-memory wavefronts -- measured slower).  lane = (row subgroup rs, K chunk ch): per step a warp
+        // covers 4 rows x 32 heliostats, each lane evaluating its 4 heliostats for one row and storing them as one
+        // 16-byte chunk, so every store instruction writes four full 128-byte rows of the swizzled tile.
         constexpr int PSX = C::kASplit;                  // = kBSplit
-        constexpr int kCh = 8 / PSX;                     // 16-byte chunks per warp and row
-        constexpr int kRS = 32 / kCh;                    // rows per step: 4 (PS = 1) or 8 (PS = 2)
-        constexpr int kSteps = 32 / kRS;
+        constexpr int kRows = 32 / PSX;                  // operand rows per warp
+        constexpr int kRS = 4;                           // rows per step
+        constexpr int kSteps = kRows / kRS;
         static_assert(PSX == 1 || PSX == 2, "producer split");
         const bool isA = warp < C::kAWarps;
         const int pw = isA ? warp : warp - C::kAWarps;                   // producer index inside its operand
-        const int wrow = (pw / PSX) * 32;                                // first operand row of this warp (CTA-local)
-        const int rs = lane / kCh, ch = (pw % PSX) * kCh + lane % kCh;
+        const int wrow = pw * kRows;                                     // first operand row of this warp (CTA-local)
+        const int rs = lane >> 3, ch = lane & 7;
         const uint32_t region = (isA ? 0u : 2u * C::kABytes) + (uint32_t)(wrow >> 3) * 1024u;
         const uint32_t lo_delta = isA ? C::kABytes : C::kBBytes;
         // rows visited by this lane: wrow + kRS*step + rs
@@ -559,9 +560,9 @@ inline cudaError_t splat_tc_fwd(const float* params, float* img, int B, int N, i
         return HELIO_FWD(256, 1, 1);
     }
     if (R > 64) return split == 2 ? HELIO_FWD(128, 1, 2) : HELIO_FWD(128, 1, 1);
-    // measured on B200: two producer warps per slab only pay off for the 64-wide tile (-11 % at N = 5000; the wider
-    // tiles are bound by shared-memory bandwidth, not producer latency, and lose 8-10 %)
-    return split == 1 ? HELIO_FWD(64, 1, 1) : HELIO_FWD(64, 1, 2);
+    // measured on B200: twice the producer warps (split = 2) is 6-25 % slower at every shape, whether the extra warps
+    // split the rows or the K range of a stage; kept as an A/B switch (HELIO_TC_FWD_SPLIT=2) only
+    return split == 2 ? HELIO_FWD(64, 1, 2) : HELIO_FWD(64, 1, 1);
 #undef HELIO_FWD
 }
 
