@@ -99,3 +99,52 @@ def test_dropin_modules_resolve():
     finally:
         sys.path.remove(os.path.join(ROOT, "dropin"))
         sys.modules.pop("newenv_rl_test_multi_error", None)
+
+
+def test_header_is_plain_c():
+    """include/helio_b200.h is the C ABI: it must compile as C99 on its own (no C++ constructs, no CUDA headers)."""
+    import shutil, subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    r = subprocess.run([gcc, "-fsyntax-only", "-x", "c", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror",
+                        os.path.join(ROOT, "include", "helio_b200.h")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
+def test_c_program_can_bind_the_library(tmp_path):
+    """A plain C host (what a non-Python maintainer would write) dlopens libhelio_sm100.so, resolves every entry point
+    declared in the header and calls the ones that need no GPU."""
+    import re, shutil, subprocess
+    from doodle_b200 import _lib
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    _lib.load(build_if_missing=True)
+    header = open(os.path.join(ROOT, "include", "helio_b200.h")).read()
+    names = sorted(set(re.findall(r"HELIO_API[^;(]*?\b(helio_[a-z0-9_]+)\s*\(", header)))
+    src = tmp_path / "bind.c"
+    src.write_text('''
+#include <dlfcn.h>
+#include <stdio.h>
+#include "helio_b200.h"
+int main(int argc, char** argv) {
+    void* h = dlopen(argv[1], RTLD_NOW | RTLD_LOCAL);
+    if (!h) { fprintf(stderr, "dlopen: %s\\n", dlerror()); return 2; }
+    const char* names[] = {''' + ", ".join(f'"{n}"' for n in names) + '''};
+    for (unsigned i = 0; i < sizeof names / sizeof names[0]; ++i)
+        if (!dlsym(h, names[i])) { fprintf(stderr, "missing %s\\n", names[i]); return 3; }
+    int (*ver)(void) = (int (*)(void))dlsym(h, "helio_abi_version");
+    long long (*wsb)(int, int) = (long long (*)(int, int))dlsym(h, "helio_geom_workspace_bytes");
+    if (ver() != HELIO_ABI_VERSION) return 4;
+    if (wsb(4, 100) <= 0 || wsb(0, 100) != 0) return 5;
+    printf("abi %d, %u symbols\\n", ver(), (unsigned)(sizeof names / sizeof names[0]));
+    return 0;
+}
+''')
+    exe = tmp_path / "bind"
+    r = subprocess.run([gcc, "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe), "-ldl"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe), _lib.LIB_PATH], capture_output=True, text=True)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    assert f"abi {_lib.ABI_VERSION}" in r.stdout
