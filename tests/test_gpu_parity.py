@@ -327,6 +327,12 @@ CASES = [
     dict(N=130, R=64, B=9, sigma=0.02, spread=30.0, off=60.0, err=5.0),     # N not a multiple of any chunk
     dict(N=1, R=16, B=1, sigma=0.1, spread=10.0, off=0.0, err=0.0),         # degenerate sizes
     dict(N=300, R=256, B=2, sigma=0.01, spread=10.0, off=80.0, err=90.0),   # 256x256 receiver (BASELINE configs[3] resolution)
+    dict(N=40, R=512, B=1, sigma=0.02, spread=10.0, off=80.0, err=60.0),    # 2x2 CTA-pair tiles per image (sweep resolution)
+    dict(N=257, R=200, B=2, sigma=0.02, spread=20.0, off=70.0, err=40.0),   # partial 256-tile, 2 heliostat blocks + 1 row in the backward
+    dict(N=20, R=130, B=2, sigma=0.05, spread=10.0, off=40.0, err=20.0),    # just above the 128 tile: mostly dead operand rows
+    dict(N=9, R=48, B=3, sigma=0.1, spread=10.0, off=0.0, err=30.0),        # smallest resolution routed to the tensor path
+    dict(N=9, R=47, B=3, sigma=0.1, spread=10.0, off=0.0, err=30.0),        # largest resolution on the CUDA-core path
+    dict(N=3, R=1000, B=1, sigma=0.05, spread=10.0, off=30.0, err=10.0),    # near the coordinate-table limit (kTcMaxR = 1024)
 ]
 
 
