@@ -635,3 +635,63 @@ def test_policy_trains_through_the_env():
     finally:
         sys.argv = argv
     assert out["alignment_loss_last"] < 0.7 * out["alignment_loss_first"], out
+
+
+def _oracle_step(env, action):
+    B = env.batch_size
+    errs = env.noisy_field._select_errors(B).cpu().numpy()
+    return orc.env_step(env.sun_pos.cpu().numpy(), action.detach().cpu().numpy(), errs, env.heliostat_pos.cpu().numpy(),
+                        env.targ_pos.cpu().numpy(), env.targ_norm.cpu().numpy(), env.targ_area, env.resolution, env.sigma_scale,
+                        env.distance_maps.cpu().numpy())
+
+
+@pytest.mark.parametrize("opts", [dict(batch_size=1), dict(batch_size=4, single_sun=True), dict(batch_size=3, new_sun_pos_every_reset=True),
+                                  dict(batch_size=3, azimuth=None, elevation=None), dict(batch_size=2, new_errors_every_reset=False)],
+                         ids=["B1_legacy_errors", "single_sun", "new_suns_every_reset", "random_hemisphere_suns", "fixed_errors"])
+def test_env_options_against_oracle(opts):
+    """Constructor options of HelioEnv (test_environment.py:177-330): B == 1 takes the legacy [N,2] error tensor
+    (newenv_rl_test_multi_error.py:340-342), single_sun repeats one sun, new_sun_pos_every_reset resamples suns and
+    rebuilds target / distance maps in reset() (broken in the reference, :378-385), azimuth=None samples the hemisphere."""
+    from doodle_b200 import HelioEnv
+    torch.manual_seed(29)
+    N, R = 7, 48
+    helio = torch.rand(N, 3, device=_dev()) * 10 + 40
+    helio[:, 2] = 0
+    env = HelioEnv(helio, torch.tensor([0., -5., 0.], device=_dev()), (15., 15.), torch.tensor([0., 1., 0.], device=_dev()),
+                   sigma_scale=0.05, error_scale_mrad=60.0, resolution=R, device="cuda:0", **opts)
+    B = env.batch_size
+    assert env.sun_pos.shape == (B, 3) and bool((env.sun_pos[:, 2] >= 0).all())
+    np.testing.assert_allclose(env.sun_pos.norm(dim=1).cpu().numpy(), np.hypot(1e4, 1e4), rtol=1e-5)
+    if opts.get("single_sun"):
+        assert bool((env.sun_pos == env.sun_pos[:1]).all())
+    sun0 = env.sun_pos.clone()
+    e0 = env.noisy_field.batch_error_angles_mrad.clone()
+    obs = env.reset()
+    assert obs["img"].shape == (B, R, R) and obs["aux"].shape == (B, 3 + 3 * N)
+    assert torch.equal(env.sun_pos, sun0) != bool(opts.get("new_sun_pos_every_reset"))
+    assert torch.equal(env.noisy_field.batch_error_angles_mrad, e0) == (opts.get("new_errors_every_reset") is False)
+    action = (env.ideal_normals + 0.02 * torch.randn_like(env.ideal_normals)).flatten(1).requires_grad_(True)
+    obs, m, mon = env.step(action)
+    (m["mse"] + m["dist"] + m["bound"] + m["alignment_loss"]).backward()
+    mo, mono, grad_o, img_o = _oracle_step(env, action)
+    np.testing.assert_allclose(obs["img"].detach().cpu().numpy(), img_o, **IMG_TOL)
+    for k in ("mse", "dist", "bound", "alignment_loss"):
+        np.testing.assert_allclose(float(m[k].detach()), float(mo[k]), rtol=3e-4, err_msg=k)
+    assert rel_err(action.grad.view(B, N, 3).cpu().numpy(), grad_o) < GRAD_TOL
+    assert mon["normals"].shape == (B, N, 3) and mon["reflected_rays"].shape == (B * N, 3) and mon["mae_image"].shape == (B, 1)
+
+
+def test_set_sun_pos_from_azimuth_elevation_resamples_and_rebuilds():
+    from doodle_b200 import HelioEnv
+    torch.manual_seed(3)
+    helio = torch.rand(5, 3, device=_dev()) * 10 + 40
+    helio[:, 2] = 0
+    env = HelioEnv(helio, torch.tensor([0., -5., 0.], device=_dev()), (15., 15.), torch.tensor([0., 1., 0.], device=_dev()),
+                   sigma_scale=0.05, resolution=48, batch_size=3, device="cuda:0")
+    dm0 = env.distance_maps.clone()
+    env.set_sun_pos_from_azimuth_elevation(120.0, 30.0)
+    from doodle_b200 import azimuth_elevation_to_primary_direction
+    axis = azimuth_elevation_to_primary_direction(120.0, 30.0, device=_dev())
+    cosang = (torch.nn.functional.normalize(env.sun_pos, dim=1) @ axis).cpu().numpy()
+    assert (cosang >= np.cos(np.radians(2.0)) - 1e-6).all()            # inside the 2-degree cone (test_environment.py:293)
+    assert env.distance_maps.shape == dm0.shape and not torch.equal(env.distance_maps, dm0)
