@@ -13,7 +13,7 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("HELIO_LIB_PATH") or os.path.join(_HERE, "libhelio_sm100.so")   # override: experiments only
 CSRC = os.path.join(_HERE, "csrc")
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 SPLAT_AUTO, SPLAT_SIMT, SPLAT_TC = 0, 1, 2
 
@@ -23,6 +23,7 @@ EXPORTS = (
     "helio_profile_enable", "helio_profile_count", "helio_profile_get",
     "helio_distance_maps_workspace_bytes", "helio_distance_maps",
     "helio_com_fwd", "helio_com_bwd",
+    "helio_cull_workspace_bytes", "helio_cull", "helio_splat_fwd_culled", "helio_splat_bwd_culled",
     "helio_loss_bwd_packed", "helio_loss_pack", "helio_step_partials_floats", "helio_step_fwd", "helio_step_bwd",
 )
 
@@ -80,6 +81,14 @@ def _declare(lib):
     lib.helio_com_fwd.argtypes = [p, i, i, i, f, p, p, p]
     lib.helio_com_bwd.restype = i
     lib.helio_com_bwd.argtypes = [p, p, p, i, i, i, f, p, p]
+    lib.helio_cull_workspace_bytes.restype = i64
+    lib.helio_cull_workspace_bytes.argtypes = [i, i]
+    lib.helio_cull.restype = i
+    lib.helio_cull.argtypes = [p, i, i, f, f, p, i64, p]
+    lib.helio_splat_fwd_culled.restype = i
+    lib.helio_splat_fwd_culled.argtypes = [p, i, i, i, f, f, p, p]
+    lib.helio_splat_bwd_culled.restype = i
+    lib.helio_splat_bwd_culled.argtypes = [p, p, i, i, i, f, f, p, p]
     lib.helio_geom_workspace_bytes.restype = i64
     lib.helio_geom_workspace_bytes.argtypes = [i, i]
     lib.helio_geom_fwd.restype = i
@@ -101,11 +110,11 @@ def _declare(lib):
     lib.helio_loss_pack.restype = i
     lib.helio_loss_pack.argtypes = [p, i, p, p]
     lib.helio_step_fwd.restype = i
-    lib.helio_step_fwd.argtypes = [sp, p, p, p, p, p, i, i, i, i, i] + [p] * 15 + [p, i64, p]
+    lib.helio_step_fwd.argtypes = [sp, p, p, p, p, p, i, i, i, i, i] + [p] * 16 + [p, i64, p]
     lib.helio_step_partials_floats.restype = i64
     lib.helio_step_partials_floats.argtypes = [i, i, i, i]
     lib.helio_step_bwd.restype = i
-    lib.helio_step_bwd.argtypes = [sp] + [p] * 9 + [i, i, i, i] + [p] * 7 + [p, p, p, p]
+    lib.helio_step_bwd.argtypes = [sp] + [p] * 9 + [i, i, i, i] + [p] * 8 + [p, p, p, p]
 
 
 def load(build_if_missing: bool = False):

@@ -5,6 +5,7 @@
 #include <vector>
 
 #include "com.cuh"
+#include "cull.cuh"
 #include "edt.cuh"
 #include "geom.cuh"
 #include "loss.cuh"
@@ -184,7 +185,7 @@ bool splat_fwd_uses_tc(int impl, int B, int N, int R) {
 }
 
 int splat_fwd_impl(const float* params, int B, int N, int R, float width, float height, float* img, int impl, void* stream,
-                   int fuse, const FwdFuse& fz) {
+                   int fuse, const FwdFuse& fz, const int* counts = nullptr) {
     const DeviceInfo* d = nullptr;
     if (int rc = require_device(&d)) return rc;
     HELIO_REQUIRE(params && img, "null pointer");
@@ -198,9 +199,9 @@ int splat_fwd_impl(const float* params, int B, int N, int R, float width, float 
             const char* e = std::getenv("HELIO_TC_FWD_SPLIT");
             return e ? std::atoi(e) : 0;
         }();
-        HELIO_CUDA_OK(splat_tc_fwd(params, img, B, N, R, width, height, d->sms, (cudaStream_t)stream, tc_pair_mode(), split, fuse, fz));
+        HELIO_CUDA_OK(splat_tc_fwd(params, img, B, N, R, width, height, d->sms, (cudaStream_t)stream, tc_pair_mode(), split, fuse, fz, counts));
     } else {
-        HELIO_REQUIRE(fuse == kFuseNone, "epilogue fusion needs the tcgen05 path");
+        HELIO_REQUIRE(fuse == kFuseNone && counts == nullptr, "epilogue fusion / culled input need the tcgen05 path");
         HELIO_CUDA_OK(splat_fwd_simt(params, img, B, N, R, width, height, d->sms, (cudaStream_t)stream));
     }
     return 0;
@@ -212,23 +213,69 @@ HELIO_API int helio_splat_fwd(const float* params, int B, int N, int R, float wi
     return splat_fwd_impl(params, B, N, R, width, height, img, impl, stream, kFuseNone, FwdFuse{});
 }
 
-HELIO_API int helio_splat_bwd(const float* params, const float* g_img, int B, int N, int R, float width, float height,
-                    float* moments, int impl, void* stream) {
+namespace {
+bool splat_bwd_uses_tc(int impl, int B, int N, int R) {
+    const bool tc_ok = splat_tc_bwd_supported(B, N, R);
+    return (impl == HELIO_SPLAT_TC && tc_ok) || (impl == HELIO_SPLAT_AUTO && tc_ok && splat_tc_bwd_preferred(B, N, R));
+}
+
+int splat_bwd_impl(const float* params, const float* g_img, int B, int N, int R, float width, float height, float* moments,
+                   int impl, void* stream, const int* counts = nullptr, const int* index = nullptr) {
     const DeviceInfo* d = nullptr;
     if (int rc = require_device(&d)) return rc;
     HELIO_REQUIRE(params && g_img && moments, "null pointer");
     HELIO_REQUIRE(B > 0 && N > 0 && R > 0, "B, N, R must be positive");
     HELIO_REQUIRE(impl >= HELIO_SPLAT_AUTO && impl <= HELIO_SPLAT_TC, "unknown impl");
     KernelTimer timer("splat_bwd", stream);
-    const bool tc_ok = splat_tc_bwd_supported(B, N, R);
-    if (impl == HELIO_SPLAT_TC && !tc_ok)
+    if (impl == HELIO_SPLAT_TC && !splat_tc_bwd_supported(B, N, R))
         return set_error(HELIO_E_BADARG, "tcgen05 splat backward does not support this shape%s%s");
-    if (impl == HELIO_SPLAT_TC || (impl == HELIO_SPLAT_AUTO && tc_ok && splat_tc_bwd_preferred(B, N, R))) {
-        HELIO_CUDA_OK(splat_tc_bwd(params, g_img, moments, B, N, R, width, height, d->sms, (cudaStream_t)stream, tc_pair_mode()));
+    if (splat_bwd_uses_tc(impl, B, N, R)) {
+        if (counts) HELIO_CUDA_OK(cudaMemsetAsync(moments, 0, (size_t)B * N * 16, (cudaStream_t)stream));   // culled heliostats: zero
+        HELIO_CUDA_OK(splat_tc_bwd(params, g_img, moments, B, N, R, width, height, d->sms, (cudaStream_t)stream, tc_pair_mode(),
+                                   counts, index));
     } else {
+        HELIO_REQUIRE(counts == nullptr, "culled input needs the tcgen05 path");
         HELIO_CUDA_OK(splat_bwd_simt(params, g_img, moments, B, N, R, width, height, d->sms, (cudaStream_t)stream));
     }
     return 0;
+}
+}  // namespace
+
+HELIO_API int helio_splat_bwd(const float* params, const float* g_img, int B, int N, int R, float width, float height,
+                    float* moments, int impl, void* stream) {
+    return splat_bwd_impl(params, g_img, B, N, R, width, height, moments, impl, stream);
+}
+
+HELIO_API int64_t helio_cull_workspace_bytes(int B, int N) { return cull_workspace_bytes(B, N); }
+
+HELIO_API int helio_cull(const float* params, int B, int N, float width, float height, void* workspace, int64_t workspace_bytes,
+               void* stream) {
+    const DeviceInfo* d = nullptr;
+    if (int rc = require_device(&d)) return rc;
+    HELIO_REQUIRE(params && workspace, "null pointer");
+    HELIO_REQUIRE(B > 0 && N > 0, "B, N must be positive");
+    if (workspace_bytes < cull_workspace_bytes(B, N)) return set_error(HELIO_E_WORKSPACE, "cull workspace too small%s%s");
+    KernelTimer timer("cull", stream);
+    cull_kernel<<<B, kCullThreads, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(params), N, 0.5f * width, 0.5f * height,
+                                                              cull_carve(workspace, B, N));
+    HELIO_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+HELIO_API int helio_splat_fwd_culled(const void* cull_workspace, int B, int N, int R, float width, float height, float* img,
+                           void* stream) {
+    HELIO_REQUIRE(cull_workspace, "null pointer");
+    const CullBuffers c = cull_carve(const_cast<void*>(cull_workspace), B, N);
+    return splat_fwd_impl(reinterpret_cast<const float*>(c.cparams), B, N, R, width, height, img, HELIO_SPLAT_TC, stream, kFuseNone,
+                          FwdFuse{}, c.counts);
+}
+
+HELIO_API int helio_splat_bwd_culled(const void* cull_workspace, const float* g_img, int B, int N, int R, float width, float height,
+                           float* moments, void* stream) {
+    HELIO_REQUIRE(cull_workspace, "null pointer");
+    const CullBuffers c = cull_carve(const_cast<void*>(cull_workspace), B, N);
+    return splat_bwd_impl(reinterpret_cast<const float*>(c.cparams), g_img, B, N, R, width, height, moments, HELIO_SPLAT_TC, stream,
+                          c.counts, c.index);
 }
 
 HELIO_API int helio_image_max(const float* target, int B, int R, float* tx, void* stream) {
@@ -366,7 +413,7 @@ HELIO_API int helio_step_fwd(const helio_scene_t* scene, const float* helio_pos,
                    const float* errs, const float* dmaps, int B, int N, int R, int impl, int render_target, float* params,
                    float* actual, float* refl, float* ideal, float* bounds, float* angles, float* img, float* target,
                    float* tx, float* per_img, float* packed, float* tgt_params, float* tgt_actual, float* tgt_refl,
-                   float* loss_partials, void* workspace, int64_t workspace_bytes, void* stream) {
+                   float* loss_partials, void* cull_workspace, void* workspace, int64_t workspace_bytes, void* stream) {
     HELIO_REQUIRE(scene && target && tx, "null pointer");
     HELIO_REQUIRE(action == nullptr || (ideal && bounds && angles && img && per_img && packed && dmaps), "null pointer");
     HELIO_REQUIRE(action != nullptr || render_target, "nothing to do");
@@ -399,12 +446,21 @@ HELIO_API int helio_step_fwd(const helio_scene_t* scene, const float* helio_pos,
     // noisy field: K1 (with ideal normals, boundary, alignment and their sums -> packed[2..3])
     if (int rc = helio_geom_fwd(scene, helio_pos, sun, action, errs, B, N, params, actual, refl, ideal, bounds, angles,
                                 packed + 2, workspace, workspace_bytes, stream)) return rc;
+    // opt-in culling: contract only over the heliostats whose footprint can reach the receiver (cull.cuh)
+    const float* sp = params;
+    const int* counts = nullptr;
+    if (cull_workspace && tc) {
+        if (int rc = helio_cull(params, B, N, scene->width, scene->height, cull_workspace, cull_workspace_bytes(B, N), stream)) return rc;
+        const CullBuffers cb = cull_carve(cull_workspace, B, N);
+        sp = reinterpret_cast<const float*>(cb.cparams);
+        counts = cb.counts;
+    }
     if (!fused)
-        if (int rc = helio_splat_fwd(params, B, N, R, scene->width, scene->height, img, impl, stream)) return rc;
+        if (int rc = splat_fwd_impl(sp, B, N, R, scene->width, scene->height, img, impl, stream, kFuseNone, FwdFuse{}, counts)) return rc;
     if (fused) {
         FwdFuse fz{};
         fz.target = target, fz.dmaps = dmaps, fz.tx = tx, fz.partials = loss_partials;
-        if (int rc = splat_fwd_impl(params, B, N, R, scene->width, scene->height, img, impl, stream, kFuseLoss, fz)) return rc;
+        if (int rc = splat_fwd_impl(sp, B, N, R, scene->width, scene->height, img, impl, stream, kFuseLoss, fz, counts)) return rc;
         KernelTimer timer("loss_pack", stream);
         loss_pack_partials_kernel<<<1, kLossThreads, 0, (cudaStream_t)stream>>>(
             loss_partials, splat_tc_fwd_partials_per_image(R, d->sms, tc_pair_mode()), B, per_img, packed);
@@ -419,17 +475,25 @@ HELIO_API int helio_step_bwd(const helio_scene_t* scene, const float* helio_pos,
                    const float* errs, const float* params, const float* img, const float* target, const float* dmaps,
                    const float* tx, int B, int N, int R, int impl, const float* g_packed, const float* g_per_img,
                    const float* g_img_in, const float* g_actual, const float* g_refl, const float* g_bounds,
-                   const float* g_angles, float* g_img, float* moments, float* g_action, void* stream) {
+                   const float* g_angles, const void* cull_workspace, float* g_img, float* moments, float* g_action,
+                   void* stream) {
     HELIO_REQUIRE(scene && params, "null pointer");
+    // culled forward: the backward visits the same compacted heliostat lists (the workspace helio_step_fwd filled)
+    const float* sp = params;
+    const int *counts = nullptr, *index = nullptr;
+    if (cull_workspace && splat_bwd_uses_tc(impl, B, N, R)) {
+        const CullBuffers cb = cull_carve(const_cast<void*>(cull_workspace), B, N);
+        sp = reinterpret_cast<const float*>(cb.cparams), counts = cb.counts, index = cb.index;
+    }
     HELIO_REQUIRE(moments || !(g_packed || g_per_img || g_img_in), "moments scratch missing");
     const float* g_mom = nullptr;
     if (g_packed || g_per_img) {
         HELIO_REQUIRE(g_img, "g_img scratch missing");
         if (int rc = helio_loss_bwd_packed(img, target, dmaps, tx, g_per_img, g_packed, g_img_in, B, R, g_img, stream)) return rc;
-        if (int rc = helio_splat_bwd(params, g_img, B, N, R, scene->width, scene->height, moments, impl, stream)) return rc;
+        if (int rc = splat_bwd_impl(sp, g_img, B, N, R, scene->width, scene->height, moments, impl, stream, counts, index)) return rc;
         g_mom = moments;
     } else if (g_img_in) {
-        if (int rc = helio_splat_bwd(params, g_img_in, B, N, R, scene->width, scene->height, moments, impl, stream)) return rc;
+        if (int rc = splat_bwd_impl(sp, g_img_in, B, N, R, scene->width, scene->height, moments, impl, stream, counts, index)) return rc;
         g_mom = moments;
     }
     return helio_geom_bwd(scene, helio_pos, sun, action, errs, B, N, g_mom, g_actual, g_refl, g_bounds, g_angles,

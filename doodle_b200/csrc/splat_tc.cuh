@@ -239,15 +239,18 @@ struct FwdFuse {
 // ahead) and every warp store writes four full 128-byte rows of the swizzled tile, conflict-free.
 template <int NT, int CG, int PS, int FUSE>
 __global__ void __launch_bounds__(SplatFwdTc<NT, CG, PS>::kThreads, 1)
-splat_fwd_tc_kernel(const float4* __restrict__ params, float* __restrict__ img, int N, int R, Axis ax, Axis ay,
-                    int tiles_i, int tiles_j, int num_tiles, FwdFuse fz) {
+splat_fwd_tc_kernel(const float4* __restrict__ params, const int* __restrict__ counts, float* __restrict__ img, int N, int R,
+                    Axis ax, Axis ay, int tiles_i, int tiles_j, int num_tiles, FwdFuse fz) {
     using C = SplatFwdTc<NT, CG, PS>;
     extern __shared__ uint8_t smem_raw[];
     SplatTcCtx<C, CG> cx;
     cx.setup(smem_raw, R, ax, ay);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nchunks = (N + C::kKC - 1) / C::kKC;
+    // heliostats contracted for sun b: all N, or the first counts[b] of a culled (compacted) parameter row; at least one
+    // (all-padding) stage so that the accumulator is always written
+    auto sun_count = [&](int b) { return counts ? __ldg(counts + b) : N; };
+    auto sun_chunks = [&](int cnt) { return max(1, (cnt + C::kKC - 1) / C::kKC); };
     const int tiles_per_img = tiles_i * tiles_j;
     const int group = blockIdx.x / CG, ngroups = gridDim.x / CG;
     constexpr int kTileM = C::kM * CG;
@@ -290,19 +293,20 @@ splat_fwd_tc_kernel(const float4* __restrict__ params, float* __restrict__ img, 
 #pragma unroll
             for (int st = 0; st < kSteps; ++st) xr[st] = tc::lds_f32(tab + 4u * kRS * st);
             const float4* pb = params + (size_t)b * N;
+            const int cnt = sun_count(b), nchunks = sun_chunks(cnt), last = max(cnt, 1) - 1;
             // this lane's 4 heliostats of the stage, prefetched one stage ahead as raw float4 (index clamped so the
             // load never needs a select: nothing touches the loaded registers until the next stage decodes them)
             float4 pr[4];
             auto prefetch = [&](int c) {
 #pragma unroll
-                for (int e = 0; e < 4; ++e) pr[e] = __ldg(pb + min(c * C::kKC + 4 * ch + e, N - 1));
+                for (int e = 0; e < 4; ++e) pr[e] = __ldg(pb + min(c * C::kKC + 4 * ch + e, last));
             };
             prefetch(0);
             for (int c = 0; c < nchunks; ++c, ++it) {
                 float ctr[4], nk2[4], la[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    const bool have = c * C::kKC + 4 * ch + e < N;
+                    const bool have = c * C::kKC + 4 * ch + e < cnt;
                     ctr[e] = isA ? pr[e].x : pr[e].y;
                     nk2[e] = -pr[e].z;
                     // amplitude folded into the exponent (amp ~ 1: lg2.approx is exact to 2^-22 absolute there);
@@ -403,6 +407,7 @@ splat_fwd_tc_kernel(const float4* __restrict__ params, float* __restrict__ img, 
             uint32_t it = 0, tcount = 0;
             for (int tile = group; tile < num_tiles; tile += ngroups, ++tcount) {
                 const int acc = tcount & 1;
+                const int nchunks = sun_chunks(sun_count(tile / tiles_per_img));
                 cx.mma_wait_tempty(acc, (tcount >> 1) & 1);
                 const uint32_t d_tmem = cx.tmem_base + (uint32_t)(acc * NT);
                 for (int c = 0; c < nchunks; ++c, ++it) {
@@ -534,16 +539,16 @@ inline int splat_tc_fwd_partials_per_image(int R, int num_sms, int pair) {
 }
 
 template <int NT, int CG, int PS>
-inline cudaError_t launch_splat_fwd_tc(const float* params, float* img, int B, int N, int R, float width, float height,
-                                       int num_sms, cudaStream_t st, int fuse, const FwdFuse& fz) {
+inline cudaError_t launch_splat_fwd_tc(const float* params, const int* counts, float* img, int B, int N, int R, float width,
+                                       float height, int num_sms, cudaStream_t st, int fuse, const FwdFuse& fz) {
     using C = SplatFwdTc<NT, CG, PS>;
     const int tiles_i = (R + C::kM * CG - 1) / (C::kM * CG), tiles_j = (R + NT - 1) / NT;
     const long long num_tiles = (long long)B * tiles_i * tiles_j;
     if (num_tiles > 0x7fffffffLL) return cudaErrorInvalidValue;
     auto go = [&](auto kernel) {
         return launch_tc_groups<CG>(kernel, num_tiles, num_sms, C::kThreads, C::kSmemBytes, st,
-                                    reinterpret_cast<const float4*>(params), img, N, R, make_axis(width, R), make_axis(height, R),
-                                    tiles_i, tiles_j, (int)num_tiles, fz);
+                                    reinterpret_cast<const float4*>(params), counts, img, N, R, make_axis(width, R),
+                                    make_axis(height, R), tiles_i, tiles_j, (int)num_tiles, fz);
     };
     if (fuse == kFuseMax) return go(splat_fwd_tc_kernel<NT, CG, PS, kFuseMax>);
     if (fuse == kFuseLoss) return go(splat_fwd_tc_kernel<NT, CG, PS, kFuseLoss>);
@@ -552,9 +557,11 @@ inline cudaError_t launch_splat_fwd_tc(const float* params, float* img, int B, i
 
 // pair = 0: auto (CTA pairs for images taller than 128 rows), 1: single CTA, 2: CTA pairs
 // split = producer warps per 32-row operand slab (1 or 2; 0 = auto)
+// counts (may be NULL): per-sun number of valid entries of a culled parameter row (cull.cuh)
 inline cudaError_t splat_tc_fwd(const float* params, float* img, int B, int N, int R, float width, float height, int num_sms,
-                                cudaStream_t st, int pair = 0, int split = 0, int fuse = kFuseNone, const FwdFuse& fz = FwdFuse{}) {
-#define HELIO_FWD(NT_, CG_, PS_) launch_splat_fwd_tc<NT_, CG_, PS_>(params, img, B, N, R, width, height, num_sms, st, fuse, fz)
+                                cudaStream_t st, int pair = 0, int split = 0, int fuse = kFuseNone, const FwdFuse& fz = FwdFuse{},
+                                const int* counts = nullptr) {
+#define HELIO_FWD(NT_, CG_, PS_) launch_splat_fwd_tc<NT_, CG_, PS_>(params, counts, img, B, N, R, width, height, num_sms, st, fuse, fz)
     if (R > 128) {
         if (splat_tc_fwd_cg(R, num_sms, pair) == 2) return split == 2 ? HELIO_FWD(256, 2, 2) : HELIO_FWD(256, 2, 1);
         return HELIO_FWD(256, 1, 1);
@@ -580,8 +587,9 @@ using SplatBwdTc = SplatTcLayout<NT, CG, NT / CG, 2>;
 
 template <int NT, int CG>
 __global__ void __launch_bounds__(SplatBwdTc<NT, CG>::kThreads, 1)
-splat_bwd_tc_kernel(const float4* __restrict__ params, const float* __restrict__ g_img, float4* __restrict__ moments,
-                    int N, int R, Axis ax, Axis ay, int nblocks, int num_tiles) {
+splat_bwd_tc_kernel(const float4* __restrict__ params, const int* __restrict__ counts, const int* __restrict__ index,
+                    const float* __restrict__ g_img, float4* __restrict__ moments, int N, int R, Axis ax, Axis ay, int nblocks,
+                    int num_tiles) {
     using C = SplatBwdTc<NT, CG>;
     extern __shared__ uint8_t smem_raw[];
     SplatTcCtx<C, CG> cx;
@@ -593,6 +601,10 @@ splat_bwd_tc_kernel(const float4* __restrict__ params, const float* __restrict__
     const bool vec = (R & 3) == 0;
     const int group = blockIdx.x / CG, ngroups = gridDim.x / CG;
     constexpr int kTileH = C::kM * CG;               // heliostats per tile
+    // culled input (cull.cuh): params rows are compacted, counts[b] entries are valid and index maps them back; a tile
+    // past the end of its sun's list is skipped by every role alike (the caller zero-fills the moments)
+    auto sun_count = [&](int b) { return counts ? __ldg(counts + b) : N; };
+    auto tile_empty = [&](int tile) { return (tile % nblocks) * kTileH >= sun_count(tile / nblocks); };
 
     if (warp < C::kAWarps) {
         // ================= Gaussian operand: thread = heliostat row, warp = (32-row slab, K slice) =================
@@ -607,7 +619,7 @@ splat_bwd_tc_kernel(const float4* __restrict__ params, const float* __restrict__
         auto tile_params = [&](int tile, bool& live) {
             const int b = tile / nblocks, nb = tile % nblocks;
             const int n = nb * kTileH + (int)cx.rank * C::kM + r;
-            live = tile < num_tiles && n < N;
+            live = tile < num_tiles && n < sun_count(b);
             return live ? __ldg(params + (size_t)b * N + n) : make_float4(0.f, 0.f, 0.f, 1.f);
         };
         bool live_next;
@@ -619,6 +631,7 @@ splat_bwd_tc_kernel(const float4* __restrict__ params, const float* __restrict__
             const bool live = live_next;
             const float4 p = p_next;
             p_next = tile_params(tile + ngroups, live_next);
+            if (tile_empty(tile)) continue;
             const float nk2 = -p.z;
             const float dead = live ? 0.f : -INFINITY;   // rows beyond N: 2^-inf = 0
 #pragma unroll 1
@@ -697,6 +710,7 @@ splat_bwd_tc_kernel(const float4* __restrict__ params, const float* __restrict__
         int spending = -1;
 #endif
         for (int tile = group; tile < num_tiles; tile += ngroups) {
+            if (tile_empty(tile)) continue;
             const int b = tile / nblocks;
             const float* gb = g_img + (size_t)b * R * R;
 #pragma unroll 1
@@ -802,6 +816,7 @@ splat_bwd_tc_kernel(const float4* __restrict__ params, const float* __restrict__
             uint32_t it = 0, sub = 0;
             const int subs_per_tile = 2 * pblocks;
             for (int tile = group; tile < num_tiles; tile += ngroups) {
+                if (tile_empty(tile)) continue;
                 for (int sb = 0; sb < subs_per_tile; ++sb, ++sub) {
                     const int acc = sub & 1;
                     cx.mma_wait_tempty(acc, (sub >> 1) & 1);
@@ -822,7 +837,7 @@ splat_bwd_tc_kernel(const float4* __restrict__ params, const float* __restrict__
         auto tile_params = [&](int tile, bool& live) {
             const int b = tile / nblocks, nb = tile % nblocks;
             const int n = nb * kTileH + (int)cx.rank * C::kM + q * 32 + lane;
-            live = tile < num_tiles && n < N;
+            live = tile < num_tiles && n < sun_count(b);
             return live ? __ldg(params + (size_t)b * N + n) : make_float4(0.f, 0.f, 0.f, 0.f);
         };
         bool live_next;
@@ -833,6 +848,7 @@ splat_bwd_tc_kernel(const float4* __restrict__ params, const float* __restrict__
             const bool live = live_next;
             const float4 p = p_next;
             p_next = tile_params(tile + ngroups, live_next);
+            if (tile_empty(tile)) continue;
             const float nk2 = -p.z;
             float S0 = 0.f, Sx = 0.f, Sy = 0.f, S2 = 0.f;
 #pragma unroll 1
@@ -876,7 +892,7 @@ splat_bwd_tc_kernel(const float4* __restrict__ params, const float* __restrict__
                     Sy = s1, S2 += s2;
                 }
             }
-            if (live) moments[(size_t)b * N + n] = make_float4(S0, Sx, Sy, S2);
+            if (live) moments[(size_t)b * N + (index ? __ldg(index + (size_t)b * N + n) : n)] = make_float4(S0, Sx, Sy, S2);
         }
     }
     cx.teardown();
@@ -886,27 +902,31 @@ inline bool splat_tc_bwd_supported(int B, int N, int R) { return B > 0 && N > 0 
 inline bool splat_tc_bwd_preferred(int B, int N, int R) { return R >= 48; }
 
 template <int NT, int CG>
-inline cudaError_t launch_splat_bwd_tc(const float* params, const float* g_img, float* moments, int B, int N, int R,
-                                       float width, float height, int num_sms, cudaStream_t st) {
+inline cudaError_t launch_splat_bwd_tc(const float* params, const int* counts, const int* index, const float* g_img, float* moments,
+                                       int B, int N, int R, float width, float height, int num_sms, cudaStream_t st) {
     using C = SplatBwdTc<NT, CG>;
     const int nblocks = (N + C::kM * CG - 1) / (C::kM * CG);
     const long long num_tiles = (long long)B * nblocks;
     if (num_tiles > 0x7fffffffLL) return cudaErrorInvalidValue;
     return launch_tc_groups<CG>(splat_bwd_tc_kernel<NT, CG>, num_tiles, num_sms, C::kThreads, C::kSmemBytes, st,
-                                reinterpret_cast<const float4*>(params), g_img, reinterpret_cast<float4*>(moments), N, R,
-                                make_axis(width, R), make_axis(height, R), nblocks, (int)num_tiles);
+                                reinterpret_cast<const float4*>(params), counts, index, g_img, reinterpret_cast<float4*>(moments),
+                                N, R, make_axis(width, R), make_axis(height, R), nblocks, (int)num_tiles);
 }
 
+// counts / index (may be NULL): culled (compacted) parameter rows and their original heliostat indices (cull.cuh); the
+// caller zero-fills `moments` first, only the kept heliostats are written
 inline cudaError_t splat_tc_bwd(const float* params, const float* g_img, float* moments, int B, int N, int R, float width,
-                                float height, int num_sms, cudaStream_t st, int pair = 0) {
+                                float height, int num_sms, cudaStream_t st, int pair = 0, const int* counts = nullptr,
+                                const int* index = nullptr) {
+#define HELIO_BWD(NT_, CG_) launch_splat_bwd_tc<NT_, CG_>(params, counts, index, g_img, moments, B, N, R, width, height, num_sms, st)
     if (R > 128) {
         // CTA pairs need a second block of 128 heliostats to be worth it
-        if (pair != 1 && num_sms >= 2 && (pair == 2 || N > 128))
-            return launch_splat_bwd_tc<256, 2>(params, g_img, moments, B, N, R, width, height, num_sms, st);
-        return launch_splat_bwd_tc<256, 1>(params, g_img, moments, B, N, R, width, height, num_sms, st);
+        if (pair != 1 && num_sms >= 2 && (pair == 2 || N > 128)) return HELIO_BWD(256, 2);
+        return HELIO_BWD(256, 1);
     }
-    if (R > 64) return launch_splat_bwd_tc<128, 1>(params, g_img, moments, B, N, R, width, height, num_sms, st);
-    return launch_splat_bwd_tc<64, 1>(params, g_img, moments, B, N, R, width, height, num_sms, st);
+    if (R > 64) return HELIO_BWD(128, 1);
+    return HELIO_BWD(64, 1);
+#undef HELIO_BWD
 }
 
 }  // namespace helio

@@ -17,6 +17,10 @@ Differences, all opt-in or bug-compatible:
     stream while the target renders, and its gradient is returned in pinned host memory, copied out slice by slice
     under the backward kernels (functional.HostStepFn); ``obs['aux']`` is then built from the device copy (no
     autograd link to the host action);
+  * ``cull`` (keyword-only, default False): the fused step contracts only over the heliostats whose footprint can
+    reach the receiver (helio_cull: every dropped term is below 2^-40 of its peak on every pixel), which is most of the
+    speed-up available when orientation errors are large; dense evaluation of every term, as in the reference, is the
+    default;
   * ``cache_target`` (keyword-only extension, default False = re-render the target every step as
     the reference does, test_environment.py:429-435).  The target only depends on ``sun_pos``, so
     caching it is exact.
@@ -139,6 +143,7 @@ class HelioEnv(_EnvBase):
                  check_finite=True,
                  fused_step=True,
                  distance_maps_impl="auto",
+                 cull=False,
                  ):
         super().__init__()
         require_cuda(torch.device(device), "HelioEnv")
@@ -172,6 +177,7 @@ class HelioEnv(_EnvBase):
         self.cache_target = cache_target
         self.check_finite = check_finite
         self.fused_step = fused_step
+        self.cull = cull                               # footprint culling in the fused step (helio_cull), off = dense
         self.host_chunks = 4                           # backward slices when the action lives in host memory
         self._copy_stream = None
         self.distance_maps_impl = distance_maps_impl   # "auto"/"cuda": GPU EDT; "scipy": the reference's host path
@@ -296,7 +302,7 @@ class HelioEnv(_EnvBase):
             img, packed, _actual, refl, ideal_normals, bounds, angles, per_img, target, tx, action_dev = HostStepFn.apply(
                 act.contiguous(), self.sun_pos, _cf(nf._select_errors(B)), nf.heliostat_positions, self.distance_maps, nf.scene(),
                 nf._geom_workspace(B), R, nf.splat_impl, nf.splat_impl if nf.splat_impl_bwd is None else nf.splat_impl_bwd,
-                cached[0], cached[1], self._copy_stream, self.host_chunks)
+                cached[0], cached[1], self._copy_stream, self.host_chunks, self.cull)
             if self.cache_target and self._target_cache is None:
                 self._target_cache = (target, tx)
             out = SimpleNamespace(refl=refl, bounds=bounds, angles=angles)
@@ -308,7 +314,7 @@ class HelioEnv(_EnvBase):
             img, packed, _actual, refl, ideal_normals, bounds, angles, per_img, target, tx = StepFn.apply(
                 normals, self.sun_pos, _cf(nf._select_errors(B)), nf.heliostat_positions, self.distance_maps, nf.scene(),
                 nf._geom_workspace(B), R, nf.splat_impl, nf.splat_impl if nf.splat_impl_bwd is None else nf.splat_impl_bwd,
-                cached[0], cached[1])
+                cached[0], cached[1], self.cull)
             if self.cache_target and self._target_cache is None:
                 self._target_cache = (target, tx)
             out = SimpleNamespace(refl=refl, bounds=bounds, angles=angles)

@@ -254,6 +254,26 @@ def _loss_partials(lib, B, N, R, impl, dev):
     return torch.empty(n, dtype=torch.float32, device=dev), True
 
 
+_LAST_CULL = None
+
+
+def _cull_workspace(lib, B, N, dev):
+    """Compacted footprints + index map + per-sun counts of helio_cull (kept for the backward)."""
+    global _LAST_CULL
+    nbytes = int(lib.helio_cull_workspace_bytes(B, N))
+    ws = torch.empty((nbytes + 3) // 4, dtype=torch.int32, device=dev)
+    _LAST_CULL = (ws, B, N)
+    return ws
+
+
+def last_cull_kept_fraction():
+    """Fraction of (sun, heliostat) pairs the most recent culled step kept (device sync; for reporting)."""
+    if _LAST_CULL is None:
+        return None
+    ws, B, N = _LAST_CULL
+    return float(ws[B * N * 5: B * N * 5 + B].sum().item()) / float(B * N)
+
+
 def _step_fwd_kernels(render_target: bool, fused: bool, tc: bool = True) -> int:
     """Kernels helio_step_fwd enqueues: K1, K2, loss_pack (+ loss_fwd when the loss is not fused into K2's epilogue)
     and, with the target render, K1, K2 (+ image_max on the CUDA-core path; the tcgen05 splat folds the maximum into
@@ -275,7 +295,7 @@ class StepFn(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, action, sun, errs, helio, dmaps, scene, workspace, R: int, impl: int, impl_bwd: int, target, tx):
+    def forward(ctx, action, sun, errs, helio, dmaps, scene, workspace, R: int, impl: int, impl_bwd: int, target, tx, cull=False):
         lib = _lib.load()
         B, N = sun.shape[0], helio.shape[0]
         dev = action.device
@@ -291,18 +311,20 @@ class StepFn(torch.autograd.Function):
             target, tx = torch.empty(B, R, R, **f32), torch.empty(B, **f32)
             scratch = torch.empty(B * N * 10, **f32)     # params, actual, refl of the target render (discarded)
         partials, tc = _loss_partials(lib, B, N, R, impl, dev)
+        cull_ws = _cull_workspace(lib, B, N, dev) if cull and tc else None
         with _Call("step_fwd", dev):
             rc = lib.helio_step_fwd(
                 C.byref(scene), _ptr(helio), _ptr(sun), _ptr(action), _ptr(errs), _ptr(dmaps), B, N, R, impl,
                 1 if render_target else 0, _ptr(params), _ptr(actual), _ptr(refl), _ptr(ideal), _ptr(bounds), _ptr(angles),
                 _ptr(img), _ptr(target), _ptr(tx), _ptr(per_img), _ptr(packed),
                 _ptr(scratch), _ptr(scratch[4 * B * N:]) if render_target else None,
-                _ptr(scratch[7 * B * N:]) if render_target else None, _ptr(partials),
+                _ptr(scratch[7 * B * N:]) if render_target else None, _ptr(partials), _ptr(cull_ws),
                 _ptr(workspace), workspace.numel() * workspace.element_size(), _stream())
         _lib.check(rc, "helio_step_fwd")
         global _LAUNCHES
-        _LAUNCHES += _step_fwd_kernels(render_target, partials is not None, tc) - 1      # _Call counted one
+        _LAUNCHES += _step_fwd_kernels(render_target, partials is not None, tc) - 1 + (1 if cull_ws is not None else 0)
         ctx.save_for_backward(action, sun, errs, helio, dmaps, params, img, target, tx)
+        ctx.cull_ws = cull_ws
         ctx.cfg = (scene, R, impl_bwd)
         ctx.set_materialize_grads(False)
         ctx.mark_non_differentiable(ideal, target, tx)
@@ -323,12 +345,12 @@ class StepFn(torch.autograd.Function):
         with _Call("step_bwd", action.device):
             rc = lib.helio_step_bwd(
                 C.byref(scene), _ptr(helio), _ptr(sun), _ptr(action), _ptr(errs), _ptr(params), _ptr(img), _ptr(target),
-                _ptr(dmaps), _ptr(tx), B, N, R, impl, *[_ptr(g) for g in gs],
+                _ptr(dmaps), _ptr(tx), B, N, R, impl, *[_ptr(g) for g in gs], _ptr(ctx.cull_ws),
                 _ptr(g_img), _ptr(moments), _ptr(g_action), _stream())
         _lib.check(rc, "helio_step_bwd")
         global _LAUNCHES
         _LAUNCHES += (1 if need_img else 0) + (1 if need_splat else 0)
-        return (g_action,) + (None,) * 11
+        return (g_action,) + (None,) * 12
 
 
 class HostStepFn(torch.autograd.Function):
@@ -345,7 +367,7 @@ class HostStepFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, action_host, sun, errs, helio, dmaps, scene, workspace, R, impl, impl_bwd, target, tx, copy_stream,
-                chunks: int):
+                chunks: int, cull=False):
         lib = _lib.load()
         B, N = sun.shape[0], helio.shape[0]
         dev = sun.device
@@ -364,6 +386,9 @@ class HostStepFn(torch.autograd.Function):
         per_img, packed = torch.empty(B, 3, **f32), torch.empty(4, **f32)
         global _LAUNCHES
         partials, tc = _loss_partials(lib, B, N, R, impl, dev)
+        cull_ws = _cull_workspace(lib, B, N, dev) if cull and tc else None
+        if cull_ws is not None:
+            chunks = 1                                   # the culled lists are indexed by the whole batch
         render_target = target is None
         nws = workspace.numel() * workspace.element_size()
         with _Call("step_fwd_host", dev):
@@ -373,15 +398,17 @@ class HostStepFn(torch.autograd.Function):
                 rc = lib.helio_step_fwd(
                     C.byref(scene), _ptr(helio), _ptr(sun), None, None, None, B, N, R, impl, 1, None, None, None, None, None, None,
                     None, _ptr(target), _ptr(tx), None, None, _ptr(scratch), _ptr(scratch[4 * B * N:]), _ptr(scratch[7 * B * N:]),
-                    _ptr(partials), _ptr(workspace), nws, _stream())
+                    _ptr(partials), None, _ptr(workspace), nws, _stream())
                 _lib.check(rc, "helio_step_fwd (target)")
             main.wait_event(landed)
             rc = lib.helio_step_fwd(
                 C.byref(scene), _ptr(helio), _ptr(sun), _ptr(action), _ptr(errs), _ptr(dmaps), B, N, R, impl, 0,
                 _ptr(params), _ptr(actual), _ptr(refl), _ptr(ideal_out), _ptr(bounds), _ptr(angles), _ptr(img), _ptr(target),
-                _ptr(tx), _ptr(per_img), _ptr(packed), None, None, None, _ptr(partials), _ptr(workspace), nws, _stream())
+                _ptr(tx), _ptr(per_img), _ptr(packed), None, None, None, _ptr(partials), _ptr(cull_ws), _ptr(workspace), nws,
+                _stream())
         _lib.check(rc, "helio_step_fwd")
-        _LAUNCHES += _step_fwd_kernels(render_target, partials is not None, tc) - 1
+        _LAUNCHES += _step_fwd_kernels(render_target, partials is not None, tc) - 1 + (1 if cull_ws is not None else 0)
+        ctx.cull_ws = cull_ws
         ctx.save_for_backward(action, sun, errs, helio, dmaps, params, img, target, tx)
         ctx.cfg = (scene, R, impl_bwd, copy_stream, max(1, min(int(chunks), B)), action_host.shape, action_host.is_pinned())
         ctx.set_materialize_grads(False)
@@ -415,7 +442,7 @@ class HostStepFn(torch.autograd.Function):
                     C.byref(scene), _ptr(helio), _ptr(sl(sun, b0, nb)), _ptr(sl(action, b0, nb)), _ptr(sl(errs, b0, nb)),
                     _ptr(sl(params, b0, nb)), _ptr(sl(img, b0, nb)), _ptr(sl(target, b0, nb)), _ptr(sl(dmaps, b0, nb)),
                     _ptr(sl(tx, b0, nb)), nb, N, R, impl, _ptr(gs[0]), _ptr(sl(gs[1], b0, nb)), _ptr(sl(gs[2], b0, nb)),
-                    _ptr(sl(gs[3], b0, nb)), _ptr(refl_g), _ptr(sl(gs[5], b0, nb)), _ptr(sl(gs[6], b0, nb)),
+                    _ptr(sl(gs[3], b0, nb)), _ptr(refl_g), _ptr(sl(gs[5], b0, nb)), _ptr(sl(gs[6], b0, nb)), _ptr(ctx.cull_ws),
                     _ptr(sl(g_img, b0, nb)), _ptr(sl(moments, b0, nb)), _ptr(sl(g_action, b0, nb)), _stream())
                 _lib.check(rc, "helio_step_bwd")
                 _LAUNCHES += (1 if need_img else 0) + (1 if need_splat else 0) + (1 if b0 else 0)
@@ -426,4 +453,4 @@ class HostStepFn(torch.autograd.Function):
                     h_grad.narrow(0, b0, nb).copy_(g_action.narrow(0, b0, nb), non_blocking=True)
         main.wait_stream(copy_stream)                 # g_action is freed on main: keep the allocator's ordering
         copy_stream.synchronize()                     # the caller owns a host tensor: it must be complete
-        return (h_grad.view(host_shape),) + (None,) * 13
+        return (h_grad.view(host_shape),) + (None,) * 14

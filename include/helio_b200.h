@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define HELIO_ABI_VERSION 3
+#define HELIO_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define HELIO_API __attribute__((visibility("default")))
@@ -133,6 +133,21 @@ HELIO_API int helio_splat_fwd(const float* params, int B, int N, int R, float wi
 HELIO_API int helio_splat_bwd(const float* params, const float* g_img, int B, int N, int R,
                     float width, float height, float* moments, int impl, void* stream);
 
+/* Footprint culling (opt-in; no reference counterpart -- the reference evaluates every heliostat on every
+ * pixel, newenv_rl_test_multi_error.py:140-148).  helio_cull compacts, per sun and in the original order,
+ * the heliostats whose Gaussian can exceed 2^-40 of its peak anywhere on the receiver:
+ *   k2 (dx^2 + dy^2) <= 40,  dx = max(|a| - width/2, 0),  dy = max(|b| - height/2, 0)   ({a,b,k2,amp} = params)
+ * into `workspace` (compacted params [B][N][4], original indices [B][N], counts [B]).  The *_culled splats
+ * (tcgen05 path only) contract over counts[b] heliostats / visit only the kept ones; culled heliostats get
+ * exactly zero moments.  Every dropped term is below amp * 2^-40 on every pixel. */
+HELIO_API int64_t helio_cull_workspace_bytes(int B, int N);
+HELIO_API int helio_cull(const float* params, int B, int N, float width, float height,
+               void* workspace, int64_t workspace_bytes, void* stream);
+HELIO_API int helio_splat_fwd_culled(const void* cull_workspace, int B, int N, int R, float width, float height,
+                           float* img, void* stream);
+HELIO_API int helio_splat_bwd_culled(const void* cull_workspace, const float* g_img, int B, int N, int R,
+                           float width, float height, float* moments, void* stream);
+
 /* tx[b] = max(max_ij target[b], 1e-6)   (test_environment.py:436). */
 HELIO_API int helio_image_max(const float* target, int B, int R, float* tx, void* stream);
 
@@ -198,7 +213,11 @@ HELIO_API int helio_loss_pack(const float* per_img, int B, float* packed, void* 
  * loss_partials (may be NULL): helio_step_partials_floats(B, N, R, impl) floats of scratch.  When given and
  * the shape takes the tcgen05 splat, image_max and loss_fwd do not run as separate passes: the target's
  * per-image maximum and the three per-image loss sums are accumulated in the splat epilogues while the
- * image rows are in registers (tx then holds the UNclamped maximum; every consumer clamps at 1e-6). */
+ * image rows are in registers (tx then holds the UNclamped maximum; every consumer clamps at 1e-6).
+ *
+ * cull_workspace (may be NULL = dense): helio_cull_workspace_bytes(B, N) bytes.  When given and the shape
+ * takes the tcgen05 splat, the noisy render contracts only over the heliostats kept by helio_cull; pass
+ * the same (untouched) workspace to helio_step_bwd. */
 HELIO_API int64_t helio_step_partials_floats(int B, int N, int R, int impl);
 HELIO_API int helio_step_fwd(const helio_scene_t* scene_host, const float* helio, const float* sun,
                    const float* action, const float* errs, const float* dmaps,
@@ -206,7 +225,7 @@ HELIO_API int helio_step_fwd(const helio_scene_t* scene_host, const float* helio
                    float* params, float* actual, float* refl, float* ideal, float* bounds, float* angles,
                    float* img, float* target, float* tx, float* per_img, float* packed,
                    float* tgt_params, float* tgt_actual, float* tgt_refl, float* loss_partials,
-                   void* workspace, int64_t workspace_bytes, void* stream);
+                   void* cull_workspace, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* Backward of helio_step_fwd down to g_action[B][N][3]: K4' (g_img) -> K3 (moments) -> K1'.
  * g_packed[4] (device) = upstream grads of packed; g_per_img[B][3], g_img_in[B][R][R] (gradient
@@ -218,7 +237,7 @@ HELIO_API int helio_step_bwd(const helio_scene_t* scene_host, const float* helio
                    int B, int N, int R, int impl,
                    const float* g_packed, const float* g_per_img, const float* g_img_in,
                    const float* g_actual, const float* g_refl, const float* g_bounds, const float* g_angles,
-                   float* g_img, float* moments, float* g_action, void* stream);
+                   const void* cull_workspace, float* g_img, float* moments, float* g_action, void* stream);
 
 #ifdef __cplusplus
 }

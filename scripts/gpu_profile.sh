@@ -3,7 +3,7 @@
 # Each ncu run is preceded by the identical plain command (must exit 0).  Everything lands in gpurun_out/.
 mkdir -p gpurun_out
 B=${PROF_B:-4096}
-BENCH="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-small-field"
+BENCH="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-small-field --no-culled"
 $BENCH > gpurun_out/prof_bench_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv $BENCH > gpurun_out/prof_bench_ncu.log 2>&1
 echo "launch list exit $?"
