@@ -177,7 +177,7 @@ class HelioEnv(_EnvBase):
         self.cache_target = cache_target
         self.check_finite = check_finite
         self.fused_step = fused_step
-        self.cull = cull                               # footprint culling in the fused step (helio_cull), off = dense
+        self.cull = cull                               # footprint culling of the noisy render (helio_cull), off = dense
         self.host_chunks = 4                           # backward slices when the action lives in host memory
         self._copy_stream = None
         self.distance_maps_impl = distance_maps_impl   # "auto"/"cuda": GPU EDT; "scipy": the reference's host path
@@ -199,6 +199,7 @@ class HelioEnv(_EnvBase):
         self.noisy_field = HelioField(error_scale_mrad=self.error_scale_mrad, **common)
         for f in (self.ref_field, self.noisy_field):
             f.set_boundary_geometry(self.targ_pos, self.targ_norm, self.targ_area)
+        self.noisy_field.cull = cull                   # composed route (error-mask / exponential-risk variants, reset)
 
         self.use_error_mask = use_error_mask
         self.error_mask_ratio = error_mask_ratio

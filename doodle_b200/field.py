@@ -64,6 +64,7 @@ class HelioField:
         self.initial_action = None
         self.splat_impl = SPLAT_AUTO        # forward splat: SPLAT_AUTO | SPLAT_SIMT | SPLAT_TC
         self.splat_impl_bwd = None          # backward splat; None = same selector as forward
+        self.cull = False                   # opt-in footprint culling in render() (cull.cuh); dense by default
         self._scene = None
         self._bnd = None
         self._workspace = {}
@@ -172,7 +173,7 @@ class HelioField:
         params, actual, refl, ideal, bounds, angles, sums = GeomFn.apply(
             normals, _cf(sun), errs, self.heliostat_positions, self.scene(), ws, want_aux)
         img = SplatFn.apply(params, self.resolution, float(self.target_width), float(self.target_height), self.splat_impl,
-                            self.splat_impl if self.splat_impl_bwd is None else self.splat_impl_bwd)
+                            self.splat_impl if self.splat_impl_bwd is None else self.splat_impl_bwd, self.cull)
         return SimpleNamespace(img=img, actual=actual, refl=refl, ideal=ideal, bounds=bounds, angles=angles, sums=sums,
                                normals=normals)
 

@@ -145,17 +145,27 @@ class GeomFn(torch.autograd.Function):
 
 
 class SplatFn(torch.autograd.Function):
-    """K2/K3: params -> img[B,R,R]; backward returns the moments tensor in the slot of params."""
+    """K2/K3: params -> img[B,R,R]; backward returns the moments tensor in the slot of params.
+
+    ``cull=True`` (shapes on the tcgen05 path only) contracts over the heliostats helio_cull keeps (see cull.cuh)."""
 
     @staticmethod
-    def forward(ctx, params, R: int, width: float, height: float, impl: int, impl_bwd: int):
+    def forward(ctx, params, R: int, width: float, height: float, impl: int, impl_bwd: int, cull: bool = False):
         lib = _lib.load()
         B, N = params.shape[0], params.shape[1]
         img = torch.empty(B, R, R, dtype=torch.float32, device=params.device)
+        cull_ws = None
+        if cull and impl != SPLAT_SIMT and impl_bwd != SPLAT_SIMT and int(lib.helio_step_partials_floats(B, N, R, impl)) > 0:
+            cull_ws = _cull_workspace(lib, B, N, params.device)
         with _Call("splat_fwd", params.device):
-            rc = lib.helio_splat_fwd(_ptr(params), B, N, R, width, height, _ptr(img), impl, _stream())
+            if cull_ws is not None:
+                _lib.check(lib.helio_cull(_ptr(params), B, N, width, height, _ptr(cull_ws), cull_ws.numel() * 4, _stream()), "helio_cull")
+                rc = lib.helio_splat_fwd_culled(_ptr(cull_ws), B, N, R, width, height, _ptr(img), _stream())
+            else:
+                rc = lib.helio_splat_fwd(_ptr(params), B, N, R, width, height, _ptr(img), impl, _stream())
         _lib.check(rc, "helio_splat_fwd")
         ctx.save_for_backward(params)
+        ctx.cull_ws = cull_ws
         ctx.cfg = (R, width, height, impl_bwd)
         return img
 
@@ -168,9 +178,12 @@ class SplatFn(torch.autograd.Function):
         g_img = _cf(g_img)
         moments = torch.empty_like(params)
         with _Call("splat_bwd", params.device):
-            rc = lib.helio_splat_bwd(_ptr(params), _ptr(g_img), B, N, R, width, height, _ptr(moments), impl, _stream())
+            if ctx.cull_ws is not None:
+                rc = lib.helio_splat_bwd_culled(_ptr(ctx.cull_ws), _ptr(g_img), B, N, R, width, height, _ptr(moments), _stream())
+            else:
+                rc = lib.helio_splat_bwd(_ptr(params), _ptr(g_img), B, N, R, width, height, _ptr(moments), impl, _stream())
         _lib.check(rc, "helio_splat_bwd")
-        return moments, None, None, None, None, None
+        return moments, None, None, None, None, None, None
 
 
 def image_max(target: torch.Tensor) -> torch.Tensor:

@@ -748,3 +748,22 @@ def test_culled_step_matches_dense_step(N, R, B, err):
         assert (counts == N).all()
     if err >= 3000.0:
         assert counts.mean() < 0.6 * N
+
+
+def test_culled_render_matches_dense_render():
+    """HelioField.cull = True on the composed route (GeomFn -> helio_cull -> culled K2 / K3)."""
+    from doodle_b200 import HelioField
+    case = dict(N=300, R=256, B=3, sigma=0.01, spread=10.0, off=80.0, err=120.0)
+    helio, sun, act, errs, w_img = _random_case(case, seed=5)
+    outs = []
+    for cull in (False, True):
+        f = HelioField(_t(helio), _t(np.float32([0., -5., 0.])), (15., 15.), _t(np.float32([0., 1., 0.])), error_scale_mrad=120.0,
+                       sigma_scale=0.01, resolution=256, device="cuda:0", max_batch_size=3)
+        f.batch_error_angles_mrad = _t(errs)
+        f.cull = cull
+        a = _t(act).requires_grad_(True)
+        img, actual = f.render(_t(sun), a, None)
+        g, = torch.autograd.grad((img * _t(w_img)).sum(), a)
+        outs.append((img.detach(), g))
+    np.testing.assert_allclose(outs[1][0].cpu().numpy(), outs[0][0].cpu().numpy(), rtol=1e-5, atol=1e-7)
+    assert rel_err(outs[1][1].cpu().numpy(), outs[0][1].cpu().numpy()) < 1e-5
