@@ -452,7 +452,7 @@ def main_ours(args):
         cpu_baseline, _ = run_cpu_sample(N, R, budget_s=args.cpu_seconds)
     # ---- opt-in footprint culling on the same workload (secondary; the headline above is the dense evaluation) ----
     culled = None
-    if not args.no_culled:
+    if not args.no_culled and world == 1:          # single-GPU side measurement (the other ranks have left by now)
         try:
             env.cull = True
             for _ in range(3):
