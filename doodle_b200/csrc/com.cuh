@@ -20,20 +20,35 @@ com_fwd_kernel(const float* __restrict__ img, int H, int W, int slices, float ep
     const size_t npix = (size_t)H * W;
     const float* x = img + (size_t)b * npix;
     float acc[3] = {0.f, 0.f, 0.f};
-    // rows are dealt to (slice, warp) pairs, lanes stride over the columns: coalesced, and the row / column
-    // coordinates never need an integer division
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = kLossThreads / 32;
-    for (int i = s * nw + wid; i < H; i += slices * nw) {
-        const float* row = x + (size_t)i * W;
-        float rs = 0.f, rx = 0.f;
-        for (int j = lane; j < W; j += 32) {
-            const float w = fmaxf(__ldg(row + j), 0.f);
-            rs += w;
-            rx = fmaf(w, (float)j, rx);
+    if ((W & 3) == 0) {
+        // flat float4 sweep (many independent loads in flight, as in the loss kernels); a float4 never straddles a row
+        const float4* x4 = reinterpret_cast<const float4*>(x);
+        const int nvec = (int)(npix / 4), wv = W / 4;
+#pragma unroll 4
+        for (int v = s * kLossThreads + threadIdx.x; v < nvec; v += slices * kLossThreads) {
+            const float4 q = __ldg(x4 + v);
+            const int i = v / wv, j = 4 * (v - i * wv);
+            const float w0 = fmaxf(q.x, 0.f), w1 = fmaxf(q.y, 0.f), w2 = fmaxf(q.z, 0.f), w3 = fmaxf(q.w, 0.f);
+            const float rs = (w0 + w1) + (w2 + w3);
+            acc[0] += rs;
+            acc[1] = fmaf(w0, (float)j, fmaf(w1, (float)(j + 1), fmaf(w2, (float)(j + 2), fmaf(w3, (float)(j + 3), acc[1]))));
+            acc[2] = fmaf(rs, (float)i, acc[2]);
         }
-        acc[0] += rs;
-        acc[1] += rx;
-        acc[2] = fmaf(rs, (float)i, acc[2]);
+    } else {
+        // rows are dealt to (slice, warp) pairs, lanes stride over the columns
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = kLossThreads / 32;
+        for (int i = s * nw + wid; i < H; i += slices * nw) {
+            const float* row = x + (size_t)i * W;
+            float rs = 0.f, rx = 0.f;
+            for (int j = lane; j < W; j += 32) {
+                const float w = fmaxf(__ldg(row + j), 0.f);
+                rs += w;
+                rx = fmaf(w, (float)j, rx);
+            }
+            acc[0] += rs;
+            acc[1] += rx;
+            acc[2] = fmaf(rs, (float)i, acc[2]);
+        }
     }
     __shared__ float sh[3 * 32];
     __shared__ float part[3];
