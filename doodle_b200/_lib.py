@@ -18,7 +18,7 @@ ABI_VERSION = 4
 SPLAT_AUTO, SPLAT_SIMT, SPLAT_TC = 0, 1, 2
 
 EXPORTS = (
-    "helio_abi_version", "helio_last_error", "helio_device_ok", "helio_set_tc_pair_mode", "helio_geom_workspace_bytes", "helio_geom_fwd",
+    "helio_abi_version", "helio_last_error", "helio_device_ok", "helio_set_tc_pair_mode", "helio_set_fwd_precision", "helio_geom_workspace_bytes", "helio_geom_fwd",
     "helio_geom_bwd", "helio_splat_fwd", "helio_splat_bwd", "helio_image_max", "helio_loss_fwd", "helio_loss_bwd",
     "helio_profile_enable", "helio_profile_count", "helio_profile_get",
     "helio_distance_maps_workspace_bytes", "helio_distance_maps",
@@ -67,6 +67,8 @@ def _declare(lib):
     lib.helio_device_ok.argtypes = []
     lib.helio_set_tc_pair_mode.restype = i
     lib.helio_set_tc_pair_mode.argtypes = [i]
+    lib.helio_set_fwd_precision.restype = i
+    lib.helio_set_fwd_precision.argtypes = [i]
     lib.helio_profile_enable.restype = i
     lib.helio_profile_enable.argtypes = [i]
     lib.helio_profile_count.restype = i

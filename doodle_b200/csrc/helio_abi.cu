@@ -64,6 +64,15 @@ std::atomic<int>& tc_pair_state() {
 }
 int tc_pair_mode() { return tc_pair_state().load(std::memory_order_relaxed); }
 
+// forward splat operand precision: 0 = 3xTF32 (default), 1 = two fp16 pieces of the 2^14-scaled Gaussians (opt-in)
+std::atomic<int>& fwd_prec_state() {
+    static std::atomic<int> mode{[]() {
+        const char* e = std::getenv("HELIO_FWD_PREC");
+        return (e && std::atoi(e) == 1) ? 1 : 0;
+    }()};
+    return mode;
+}
+
 // ---- opt-in per-kernel timing (helio_profile_*): CUDA events recorded around every kernel this library
 // enqueues, on the stream it is enqueued on.  Off by default; not for use under stream capture.
 struct ProfRecord {
@@ -138,6 +147,12 @@ HELIO_API int helio_profile_get(int index, const char** name, float* ms) {
     return 0;
 }
 
+HELIO_API int helio_set_fwd_precision(int mode) {
+    if (mode != 0 && mode != 1) return set_error(HELIO_E_BADARG, "bad argument: %s%s", "forward precision mode must be 0 or 1");
+    fwd_prec_state().store(mode, std::memory_order_relaxed);
+    return 0;
+}
+
 HELIO_API int64_t helio_geom_workspace_bytes(int B, int N) {
     if (B <= 0 || N <= 0) return 0;
     return (int64_t)sizeof(GeomWorkspace) + (int64_t)geom_blocks(B, N) * 2 * sizeof(float);
@@ -199,7 +214,8 @@ int splat_fwd_impl(const float* params, int B, int N, int R, float width, float 
             const char* e = std::getenv("HELIO_TC_FWD_SPLIT");
             return e ? std::atoi(e) : 0;
         }();
-        HELIO_CUDA_OK(splat_tc_fwd(params, img, B, N, R, width, height, d->sms, (cudaStream_t)stream, tc_pair_mode(), split, fuse, fz, counts));
+        HELIO_CUDA_OK(splat_tc_fwd(params, img, B, N, R, width, height, d->sms, (cudaStream_t)stream, tc_pair_mode(), split, fuse, fz, counts,
+                                   fwd_prec_state().load(std::memory_order_relaxed)));
     } else {
         HELIO_REQUIRE(fuse == kFuseNone && counts == nullptr, "epilogue fusion / culled input need the tcgen05 path");
         HELIO_CUDA_OK(splat_fwd_simt(params, img, B, N, R, width, height, d->sms, (cudaStream_t)stream));

@@ -49,7 +49,7 @@ constexpr int kTcMaxR = 1024;  // coordinate tables live in shared memory
 // ------------------------------------------------------------------------------------------------
 // pieces shared by both kernels
 // ------------------------------------------------------------------------------------------------
-template <int NT, int CG, int BROWS, int ASPLIT, int BSPLIT = 1>
+template <int NT, int CG, int BROWS, int ASPLIT, int BSPLIT = 1, int TILES = 2>
 struct SplatTcLayout {
     static constexpr int kNT = NT;                       // UMMA N (accumulator columns)
     static constexpr int kM = 128;                       // A rows per CTA = TMEM lanes
@@ -64,12 +64,16 @@ struct SplatTcLayout {
     static constexpr int kThreads = (kEpiWarp0 + 4) * 32;
     static constexpr int kABytes = kM * 128;             // one of {hi, lo}
     static constexpr int kBBytes = kBRows * 128;
-    static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
+    // TILES = 2: {hi, lo} tf32 tiles per operand (3xTF32).  TILES = 1: one tile per operand whose 128-byte rows hold
+    // two fp16 pieces of the 32 K values, [piece 1 | piece 2] (forward "f16x3" variant, see splat_fwd_tc_kernel).
+    static constexpr int kTiles = TILES;
+    static constexpr int kBOff = TILES * kABytes;        // byte offset of the B tiles inside a stage
+    static constexpr int kStageBytes = TILES * (kABytes + kBBytes);
     static constexpr int kTmemCols = 2 * NT;             // two accumulators
     static constexpr int kTableBytes = 2 * kTcMaxR * 4;
     static constexpr int kFixedBytes = kTableBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
     static constexpr int kFit = (227 * 1024 - kFixedBytes) / kStageBytes;
-    static constexpr int kStages = kFit > 4 ? 4 : kFit;
+    static constexpr int kStages = kFit > (TILES == 1 ? 6 : 4) ? (TILES == 1 ? 6 : 4) : kFit;
     static constexpr int kSmemBytes = kStages * kStageBytes + kFixedBytes;
     static constexpr int kFullCount = (kAWarps + kBWarps) * CG;   // one arrival per producer warp of the pair
     static constexpr int kTEmptyCount = 4 * CG;                   // one arrival per epilogue warp of the pair
@@ -77,6 +81,7 @@ struct SplatTcLayout {
     static_assert(BROWS * CG == NT, "each CTA of the group stages NT / CG rows of B");
     static_assert(kTmemCols <= 512 && (kTmemCols & (kTmemCols - 1)) == 0 && kTmemCols >= 32, "TMEM columns");
     static_assert(kStages >= 2 && kSmemBytes <= 227 * 1024, "shared memory budget");
+    static_assert((2 * kStages + 4) * 8 + 8 <= 256, "barrier block");
 };
 
 // shared-memory carve-up + one-time setup common to the forward and backward kernels
@@ -172,8 +177,34 @@ struct SplatTcCtx {
     }
     // MMA thread: one stage = 4 K-steps x {hi*hi, hi*lo, lo*hi}; `first` clears the accumulator
     __device__ __forceinline__ void issue_stage(int s, uint32_t d_tmem, bool first, bool last, int acc) const {
-        constexpr uint32_t idesc = tc::make_idesc_tf32(C::kM * CG, C::kNT);
         const uint32_t sa = smem_u + (uint32_t)(s * C::kStageBytes);
+        if constexpr (C::kTiles == 1) {
+            // fp16 pieces: rows are [a1 (K 0..31, 64 B) | a2 (64 B)]; products a1 b1 + a1 b2 + a2 b1, K = 16 (32 bytes) per MMA
+            constexpr uint32_t idesc16 = tc::make_idesc_f16(C::kM * CG, C::kNT);
+            const uint64_t a = tc::make_desc_k_sw128(sa), b = tc::make_desc_k_sw128(sa + C::kBOff);
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+                const uint64_t o = (uint64_t)(ks * 2);           // +32 bytes per K step (descriptor units of 16 bytes)
+                if constexpr (CG == 2) {
+                    tc::mma_f16_ss_2cta(d_tmem, a + o, b + o, idesc16, !(first && ks == 0));
+                    tc::mma_f16_ss_2cta(d_tmem, a + o, b + 4 + o, idesc16, 1);
+                    tc::mma_f16_ss_2cta(d_tmem, a + 4 + o, b + o, idesc16, 1);
+                } else {
+                    tc::mma_f16_ss(d_tmem, a + o, b + o, idesc16, !(first && ks == 0));
+                    tc::mma_f16_ss(d_tmem, a + o, b + 4 + o, idesc16, 1);
+                    tc::mma_f16_ss(d_tmem, a + 4 + o, b + o, idesc16, 1);
+                }
+            }
+            if constexpr (CG == 2) {
+                tc::mma_commit_2cta(&empty[s], 3);
+                if (last) tc::mma_commit_2cta(&tfull[acc], 3);
+            } else {
+                tc::mma_commit(&empty[s]);
+                if (last) tc::mma_commit(&tfull[acc]);
+            }
+            return;
+        }
+        constexpr uint32_t idesc = tc::make_idesc_tf32(C::kM * CG, C::kNT);
         const uint64_t a_hi = tc::make_desc_k_sw128(sa);
         const uint64_t a_lo = tc::make_desc_k_sw128(sa + C::kABytes);
         const uint64_t b_hi = tc::make_desc_k_sw128(sa + 2 * C::kABytes);
@@ -214,8 +245,13 @@ struct SplatTcCtx {
 // ================================================================================================
 // forward
 // ================================================================================================
-template <int NT, int CG, int PS>
-using SplatFwdTc = SplatTcLayout<NT, CG, NT / CG, PS, PS>;
+// PREC = 0: 3xTF32 (tf32 hi/lo tiles).  PREC = 1 ("f16x3", opt-in): both operands are Gaussians in [0, 1], so they are
+// scaled by 2^14 (exponent offset, exact) and split into two fp16 pieces v = p1 + p2 (11 + 11 significant bits, the same
+// 2^-22 the tf32 hi/lo split keeps, for every value above 2^-17; absolute error < 2^-39 below); the three products
+// p1 q1 + p1 q2 + p2 q1 run as kind::f16 MMAs at twice the tf32 rate on half the operand bytes (32 KB stages: six fit),
+// and the epilogue unscales by 2^-28.  The image gradient in the backward has no such bound, so K3 stays 3xTF32.
+template <int NT, int CG, int PS, int PREC = 0>
+using SplatFwdTc = SplatTcLayout<NT, CG, NT / CG, PS, PS, PREC == 1 ? 1 : 2>;
 
 // Work fused into the forward epilogue while the accumulator row sits in registers (the kernel is tensor-bound and
 // leaves HBM almost idle, so the HBM-bound passes of the loss block ride along for free):
@@ -237,11 +273,11 @@ struct FwdFuse {
 // 4 consecutive heliostats of the stage (one 16-byte chunk of the K-major row) and walks 8 of the
 // rows, so the footprint parameters sit in registers (loaded once per stage, prefetched one stage
 // ahead) and every warp store writes four full 128-byte rows of the swizzled tile, conflict-free.
-template <int NT, int CG, int PS, int FUSE>
-__global__ void __launch_bounds__(SplatFwdTc<NT, CG, PS>::kThreads, 1)
+template <int NT, int CG, int PS, int FUSE, int PREC>
+__global__ void __launch_bounds__(SplatFwdTc<NT, CG, PS, PREC>::kThreads, 1)
 splat_fwd_tc_kernel(const float4* __restrict__ params, const int* __restrict__ counts, float* __restrict__ img, int N, int R,
                     Axis ax, Axis ay, int tiles_i, int tiles_j, int num_tiles, FwdFuse fz) {
-    using C = SplatFwdTc<NT, CG, PS>;
+    using C = SplatFwdTc<NT, CG, PS, PREC>;
     extern __shared__ uint8_t smem_raw[];
     SplatTcCtx<C, CG> cx;
     cx.setup(smem_raw, R, ax, ay);
@@ -271,7 +307,7 @@ splat_fwd_tc_kernel(const float4* __restrict__ params, const int* __restrict__ c
         const int pw = isA ? warp : warp - C::kAWarps;                   // producer index inside its operand
         const int wrow = pw * kRows;                                     // first operand row of this warp (CTA-local)
         const int rs = lane >> 3, ch = lane & 7;
-        const uint32_t region = (isA ? 0u : 2u * C::kABytes) + (uint32_t)(wrow >> 3) * 1024u;
+        const uint32_t region = (isA ? 0u : (uint32_t)C::kBOff) + (uint32_t)(wrow >> 3) * 1024u;
         const uint32_t lo_delta = isA ? C::kABytes : C::kBBytes;
         // rows visited by this lane: wrow + kRS*step + rs
         auto row_off = [&](int st) -> uint32_t {
@@ -311,7 +347,7 @@ splat_fwd_tc_kernel(const float4* __restrict__ params, const int* __restrict__ c
                     nk2[e] = -pr[e].z;
                     // amplitude folded into the exponent (amp ~ 1: lg2.approx is exact to 2^-22 absolute there);
                     // K padding: 2^-inf = exact zeros
-                    la[e] = have ? (isA ? __log2f(pr[e].w) : 0.f) : -INFINITY;
+                    la[e] = have ? (isA ? __log2f(pr[e].w) : 0.f) + (PREC == 1 ? 14.f : 0.f) : -INFINITY;   // f16x3: operands x 2^14
                 }
                 prefetch(c + 1 < nchunks ? c + 1 : c);
                 const int s = it % C::kStages;
@@ -355,6 +391,24 @@ splat_fwd_tc_kernel(const float4* __restrict__ params, const int* __restrict__ c
                 if (pending >= 0) cx.producer_commit(pending);
                 cx.producer_acquire(s, (it / C::kStages) & 1);
                 const uint32_t base = cx.smem_u + (uint32_t)(s * C::kStageBytes) + region;
+                if constexpr (PREC == 1) {
+                    // two fp16 pieces per value, packed [p1 (8 bytes) ... | p2 ...]: this lane's 4 heliostats are bytes
+                    // 8 ch .. 8 ch + 7 of the first 64 bytes of the row (p1) and of the second 64 bytes (p2)
+                    if (!dead) {
+#pragma unroll
+                        for (int st = 0; st < kSteps; ++st) {
+                            const uint32_t p1a = tc::f2h2(v[st][0], v[st][1]), p1b = tc::f2h2(v[st][2], v[st][3]);
+                            float f0, f1, f2, f3;
+                            tc::h22f(p1a, f0, f1);
+                            tc::h22f(p1b, f2, f3);
+                            const uint32_t p2a = tc::f2h2(v[st][0] - f0, v[st][1] - f1), p2b = tc::f2h2(v[st][2] - f2, v[st][3] - f3);
+                            const uint32_t row = (uint32_t)(kRS * st + rs), sw = row & 7u;
+                            const uint32_t rb = base + (row >> 3) * 1024u + sw * 128u + 8u * ((uint32_t)ch & 1u);
+                            tc::sts_v2_b32(rb + ((((uint32_t)ch >> 1) ^ sw) << 4), p1a, p1b);
+                            tc::sts_v2_b32(rb + (((4u + ((uint32_t)ch >> 1)) ^ sw) << 4), p2a, p2b);
+                        }
+                    }
+                } else
                 if (!dead) {
 #pragma unroll
                     for (int st = 0; st < kSteps; ++st) {
@@ -378,6 +432,7 @@ splat_fwd_tc_kernel(const float4* __restrict__ params, const int* __restrict__ c
                 }
                 pending = s;
 #else
+                static_assert(PREC == 0, "the f16x3 producers are written for the deferred hand-off");
                 cx.producer_acquire(s, (it / C::kStages) & 1);
                 const uint32_t base = cx.smem_u + (uint32_t)(s * C::kStageBytes) + region;
                 if (!dead)
@@ -441,6 +496,10 @@ splat_fwd_tc_kernel(const float4* __restrict__ params, const int* __restrict__ c
                 if (j0 + cb >= R) break;
                 float v[32];
                 tc::tmem_ld_32x32(taddr + cb, v);
+                if constexpr (PREC == 1) {               // f16x3: both operands carried a factor 2^14
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) v[e] *= 3.7252902984619140625e-09f;   // 2^-28, exact
+                }
                 if (i < R) {
                     const bool full = vec && j0 + cb + 32 <= R;
                     if (full) {
@@ -538,10 +597,10 @@ inline int splat_tc_fwd_partials_per_image(int R, int num_sms, int pair) {
     return tiles * cg * 4;
 }
 
-template <int NT, int CG, int PS>
+template <int NT, int CG, int PS, int PREC = 0>
 inline cudaError_t launch_splat_fwd_tc(const float* params, const int* counts, float* img, int B, int N, int R, float width,
                                        float height, int num_sms, cudaStream_t st, int fuse, const FwdFuse& fz) {
-    using C = SplatFwdTc<NT, CG, PS>;
+    using C = SplatFwdTc<NT, CG, PS, PREC>;
     const int tiles_i = (R + C::kM * CG - 1) / (C::kM * CG), tiles_j = (R + NT - 1) / NT;
     const long long num_tiles = (long long)B * tiles_i * tiles_j;
     if (num_tiles > 0x7fffffffLL) return cudaErrorInvalidValue;
@@ -550,9 +609,9 @@ inline cudaError_t launch_splat_fwd_tc(const float* params, const int* counts, f
                                     reinterpret_cast<const float4*>(params), counts, img, N, R, make_axis(width, R),
                                     make_axis(height, R), tiles_i, tiles_j, (int)num_tiles, fz);
     };
-    if (fuse == kFuseMax) return go(splat_fwd_tc_kernel<NT, CG, PS, kFuseMax>);
-    if (fuse == kFuseLoss) return go(splat_fwd_tc_kernel<NT, CG, PS, kFuseLoss>);
-    return go(splat_fwd_tc_kernel<NT, CG, PS, kFuseNone>);
+    if (fuse == kFuseMax) return go(splat_fwd_tc_kernel<NT, CG, PS, kFuseMax, PREC>);
+    if (fuse == kFuseLoss) return go(splat_fwd_tc_kernel<NT, CG, PS, kFuseLoss, PREC>);
+    return go(splat_fwd_tc_kernel<NT, CG, PS, kFuseNone, PREC>);
 }
 
 // pair = 0: auto (CTA pairs for images taller than 128 rows), 1: single CTA, 2: CTA pairs
@@ -560,8 +619,18 @@ inline cudaError_t launch_splat_fwd_tc(const float* params, const int* counts, f
 // counts (may be NULL): per-sun number of valid entries of a culled parameter row (cull.cuh)
 inline cudaError_t splat_tc_fwd(const float* params, float* img, int B, int N, int R, float width, float height, int num_sms,
                                 cudaStream_t st, int pair = 0, int split = 0, int fuse = kFuseNone, const FwdFuse& fz = FwdFuse{},
-                                const int* counts = nullptr) {
+                                const int* counts = nullptr, int prec = 0) {
 #define HELIO_FWD(NT_, CG_, PS_) launch_splat_fwd_tc<NT_, CG_, PS_>(params, counts, img, B, N, R, width, height, num_sms, st, fuse, fz)
+    if (prec == 1) {                                 // opt-in f16x3 operands (see SplatFwdTc)
+#define HELIO_FWD16(NT_, CG_, PS_) launch_splat_fwd_tc<NT_, CG_, PS_, 1>(params, counts, img, B, N, R, width, height, num_sms, st, fuse, fz)
+        if (R > 128) {
+            if (splat_tc_fwd_cg(R, num_sms, pair) == 2) return split == 2 ? HELIO_FWD16(256, 2, 2) : HELIO_FWD16(256, 2, 1);
+            return HELIO_FWD16(256, 1, 1);
+        }
+        if (R > 64) return split == 2 ? HELIO_FWD16(128, 1, 2) : HELIO_FWD16(128, 1, 1);
+        return HELIO_FWD16(64, 1, 1);
+#undef HELIO_FWD16
+    }
     if (R > 128) {
         if (splat_tc_fwd_cg(R, num_sms, pair) == 2) return split == 2 ? HELIO_FWD(256, 2, 2) : HELIO_FWD(256, 2, 1);
         return HELIO_FWD(256, 1, 1);

@@ -71,6 +71,13 @@ HELIO_API int helio_device_ok(void);
  * No reference counterpart (tuning / A-B switch of this library). */
 HELIO_API int helio_set_tc_pair_mode(int mode);
 
+/* Forward splat operand format on the tcgen05 path.  0 (default): 3xTF32.  1 (opt-in, experimental): both
+ * operands of the forward are Gaussians in [0,1]; they are scaled by 2^14 and split into two fp16 pieces
+ * (11 + 11 significant bits, the accuracy the tf32 hi/lo split keeps), three kind::f16 MMAs per K-step,
+ * fp32 accumulation, exact 2^-28 unscale in the epilogue.  Process-wide; initial value from HELIO_FWD_PREC.
+ * The backward (unbounded image gradient) always uses 3xTF32. */
+HELIO_API int helio_set_fwd_precision(int mode);
+
 /* Opt-in per-kernel timing (no reference counterpart; SURVEY.md section 5 "tracing / profiling").
  * helio_profile_enable(1) clears earlier records and makes every entry point record a CUDA event pair
  * around each kernel it enqueues, on the caller's stream; helio_profile_enable(0) stops and clears.

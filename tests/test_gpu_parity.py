@@ -767,3 +767,35 @@ def test_culled_render_matches_dense_render():
         outs.append((img.detach(), g))
     np.testing.assert_allclose(outs[1][0].cpu().numpy(), outs[0][0].cpu().numpy(), rtol=1e-5, atol=1e-7)
     assert rel_err(outs[1][1].cpu().numpy(), outs[0][1].cpu().numpy()) < 1e-5
+
+
+def test_forward_f16x3_operands_match_reference_tolerance():
+    """helio_set_fwd_precision(1): the forward splat's Gaussian operands as two fp16 pieces of the 2^14-scaled values
+    (three kind::f16 MMAs per K-step) instead of tf32 hi/lo.  Checked against the fp64 oracle at the same tolerance as
+    the default, at several tile shapes, and it must not be less accurate than 3xTF32 by more than rounding noise."""
+    from doodle_b200 import HelioField, _lib
+    lib = _lib.load()
+    worst = {}
+    try:
+        for case in (dict(N=300, R=256, B=2, sigma=0.01, spread=10.0, off=80.0, err=90.0), dict(N=130, R=64, B=3, sigma=0.02, spread=30.0, off=60.0, err=5.0),
+                     dict(N=50, R=128, B=4, sigma=0.1, spread=10.0, off=0.0, err=90.0), dict(N=40, R=512, B=1, sigma=0.02, spread=10.0, off=80.0, err=60.0),
+                     dict(N=257, R=200, B=2, sigma=0.005, spread=20.0, off=70.0, err=10.0)):
+            helio, sun, act, errs, w_img = _random_case(case, seed=9)
+            R, B = case["R"], case["B"]
+            (img64, _, _), _ = orc.render_forward(sun, act, errs, helio, [0., -5., 0.], [0., 1., 0.], (15., 15.), R, case["sigma"],
+                                                  dtype=np.float64, keep=True)
+            for prec in (0, 1):
+                assert lib.helio_set_fwd_precision(prec) == 0
+                f = HelioField(_t(helio), _t(np.float32([0., -5., 0.])), (15., 15.), _t(np.float32([0., 1., 0.])), error_scale_mrad=case["err"],
+                               sigma_scale=case["sigma"], resolution=R, device="cuda:0", max_batch_size=max(B, 2))
+                f.batch_error_angles_mrad = _t(errs)
+                f.error_angles_mrad = _t(errs[0])
+                f.splat_impl = 2
+                img, _ = f.render(_t(sun) if B > 1 else _t(sun[0]), _t(act), None)
+                got = img.view(B, R, R).cpu().numpy().astype(np.float64)
+                ratio = float((np.abs(got - img64) / (1e-6 + 1e-4 * np.abs(img64))).max())
+                assert ratio < 1.0, (case, prec, ratio)
+                worst.setdefault(prec, []).append(ratio)
+    finally:
+        lib.helio_set_fwd_precision(0)
+    assert max(worst[1]) <= 2.0 * max(worst[0]) + 0.02, worst
