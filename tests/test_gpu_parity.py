@@ -799,3 +799,34 @@ def test_forward_f16x3_operands_match_reference_tolerance():
     finally:
         lib.helio_set_fwd_precision(0)
     assert max(worst[1]) <= 2.0 * max(worst[0]) + 0.02, worst
+
+
+def test_opt_in_switches_compose():
+    """Culling + f16x3 forward operands + cached target + host action together still reproduce the default dense step."""
+    from doodle_b200 import HelioEnv, _lib
+    lib = _lib.load()
+    res = []
+    try:
+        for fast in (False, True):
+            assert lib.helio_set_fwd_precision(1 if fast else 0) == 0
+            torch.manual_seed(77)
+            N, R, B = 200, 256, 3
+            helio = torch.rand(N, 3, device=_dev()) * 10 + 80
+            helio[:, 2] = 0
+            env = HelioEnv(helio, torch.tensor([0., -5., 0.], device=_dev()), (15., 15.), torch.tensor([0., 1., 0.], device=_dev()),
+                           sigma_scale=0.01, error_scale_mrad=120.0, resolution=R, batch_size=B, device="cuda:0", cull=fast,
+                           cache_target=fast)
+            env.reset()
+            a0 = (env.ideal_normals + 0.01 * torch.randn_like(env.ideal_normals)).flatten(1)
+            for rep in range(2 if fast else 1):
+                a = (a0.cpu().pin_memory() if fast else a0.clone()).requires_grad_(True)
+                obs, m, mon = env.step(a)
+                (m["mse"] + 0.01 * m["dist"] + m["bound"] + m["alignment_loss"]).backward()
+            res.append((obs["img"].detach().cpu(), {k: float(v.detach()) for k, v in m.items()}, a.grad.cpu()))
+    finally:
+        lib.helio_set_fwd_precision(0)
+    (i1, m1, g1), (i2, m2, g2) = res
+    np.testing.assert_allclose(i2.numpy(), i1.numpy(), rtol=1e-4, atol=1e-6)
+    for k in m1:
+        np.testing.assert_allclose(m2[k], m1[k], rtol=1e-4, err_msg=k)
+    assert rel_err(g2.numpy(), g1.numpy()) < 1e-4
