@@ -12,7 +12,7 @@ Differences, all opt-in or bug-compatible:
   * the six NaN/Inf asserts (test_environment.py:495-501) read ONE fused device flag (one sync);
   * ``fused_step`` (keyword-only, default True): ``step`` runs as one C-ABI call forward and one backward
     (helio_step_fwd / helio_step_bwd: the same kernels, far less host time for small fields); the
-    error-mask and exponential-risk variants take the composed path;
+    error-mask and exponential-risk variants are formed from its per-image sums / per-heliostat bounds;
   * a HOST action (CPU tensor or np.ndarray, which the reference accepts too, :411-412) is copied in on a side
     stream while the target renders, and its gradient is returned in pinned host memory, copied out slice by slice
     under the backward kernels (functional.HostStepFn); ``obs['aux']`` is then built from the device copy (no
@@ -286,7 +286,7 @@ class HelioEnv(_EnvBase):
     def step(self, action):
         """obs, metrics, monitor = step(action)   (:402-516).  action: [B, 3N] or [B, N, 3]."""
         B, N, R = self.batch_size, self.num_heliostats, self.resolution
-        fused = self.fused_step and not self.use_error_mask and not self.exponential_risk
+        fused = self.fused_step
         if isinstance(action, np.ndarray):                                           # :411-412
             action = torch.from_numpy(np.ascontiguousarray(action, dtype=np.float32))
         if not fused and action.device.type == "cpu":
@@ -328,18 +328,18 @@ class HelioEnv(_EnvBase):
         aux = torch.cat([self.sun_pos.detach(), action_dev.flatten(1)], dim=1)
         avg_error_per_heatmap = per_img[:, 2] / float(R * R)
 
-        if packed is None:
-            if self.use_error_mask:                                                      # :445-452
+        if packed is None or self.use_error_mask or self.exponential_risk:
+            # variants of the loss block (test_environment.py:445-452, :472-480) formed from the per-image sums and the
+            # per-heliostat bounds; autograd carries their gradients back into the same backward kernels
+            if self.use_error_mask:
                 cutoff = self._quantile_cutoff(avg_error_per_heatmap)
                 mask = (avg_error_per_heatmap > cutoff).float()
                 sq, ds = per_img[:, 0] * mask, per_img[:, 1] * mask
             else:
                 sq, ds = per_img[:, 0], per_img[:, 1]
-            if not self.exponential_risk:                                                # :464-480
-                bound_sum = out.sums[0]
-            else:
-                bound_sum = torch.exp(out.bounds + 1e-6).sum()
-            packed = torch.stack([sq.sum(), ds.sum(), bound_sum, out.sums[1]])
+            sums = packed[2:] if packed is not None else out.sums
+            bound_sum = torch.exp(out.bounds + 1e-6).sum() if self.exponential_risk else sums[0]
+            packed = torch.stack([sq.sum(), ds.sum(), bound_sum, sums[1]])
         means = self._reduce_means(packed)
         mse, dist_l, bound, alignment_loss = means.unbind(0)
 

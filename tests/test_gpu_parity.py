@@ -90,8 +90,6 @@ def _env_from_golden(g, **kw):
 @pytest.mark.parametrize("fused", [True, False], ids=["fused", "composed"])
 def test_env_step_matches_reference(name, cache, fused):
     g = load_golden("env_" + name)
-    if not fused and name in ("mask", "exprisk"):
-        pytest.skip("these variants always take the composed path")
     env = _env_from_golden(g, cache_target=cache, fused_step=fused)
     B, R = int(g["B"]), int(g["R"])
     # set_sun_pos products (test_environment.py:359-370): target render -> threshold at 0.5*max -> scipy EDT.
