@@ -49,7 +49,7 @@ constexpr int kTcMaxR = 1024;  // coordinate tables live in shared memory
 // ------------------------------------------------------------------------------------------------
 // pieces shared by both kernels
 // ------------------------------------------------------------------------------------------------
-template <int NT, int CG, int BROWS, int ASPLIT, int BSPLIT = 1, int TILES = 2>
+template <int NT, int CG, int BROWS, int ASPLIT, int BSPLIT = 1, int TILES = 2, int EPI_BYTES = 0>
 struct SplatTcLayout {
     static constexpr int kNT = NT;                       // UMMA N (accumulator columns)
     static constexpr int kM = 128;                       // A rows per CTA = TMEM lanes
@@ -71,7 +71,8 @@ struct SplatTcLayout {
     static constexpr int kStageBytes = TILES * (kABytes + kBBytes);
     static constexpr int kTmemCols = 2 * NT;             // two accumulators
     static constexpr int kTableBytes = 2 * kTcMaxR * 4;
-    static constexpr int kFixedBytes = kTableBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
+    static constexpr int kEpiBytes = EPI_BYTES;          // epilogue staging (forward: 4 warps x 32 rows x 128 B)
+    static constexpr int kFixedBytes = kTableBytes + 1024 /*alignment slack*/ + 256 /*barriers*/ + EPI_BYTES;
     static constexpr int kFit = (227 * 1024 - kFixedBytes) / kStageBytes;
     static constexpr int kStages = kFit > (TILES == 1 ? 6 : 4) ? (TILES == 1 ? 6 : 4) : kFit;
     static constexpr int kSmemBytes = kStages * kStageBytes + kFixedBytes;
@@ -92,6 +93,7 @@ struct SplatTcCtx {
     float *sX, *sY;       // pixel-centre tables
     uint32_t sX_u, sY_u;
     uint64_t *full, *empty, *tfull, *tempty;
+    uint32_t epi_u;       // epilogue staging buffer (32-bit shared address)
     uint32_t tmem_base;
     uint32_t rank;        // CTA rank inside the pair (0 when CG == 1)
 
@@ -106,6 +108,7 @@ struct SplatTcCtx {
         tfull = bars + 2 * C::kStages;     // [2]        MMA -> epilogue
         tempty = tfull + 2;                // [2]        epilogue -> MMA   (leader's copy is the live one)
         uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+        epi_u = tc::smem_u32(reinterpret_cast<uint8_t*>(bars) + 256);
         rank = CG == 2 ? tc::cluster_ctarank() : 0u;
         const int warp = threadIdx.x >> 5;
 
@@ -250,8 +253,8 @@ struct SplatTcCtx {
 // 2^-22 the tf32 hi/lo split keeps, for every value above 2^-17; absolute error < 2^-39 below); the three products
 // p1 q1 + p1 q2 + p2 q1 run as kind::f16 MMAs at twice the tf32 rate on half the operand bytes (32 KB stages: six fit),
 // and the epilogue unscales by 2^-28.  The image gradient in the backward has no such bound, so K3 stays 3xTF32.
-template <int NT, int CG, int PS, int PREC = 0>
-using SplatFwdTc = SplatTcLayout<NT, CG, NT / CG, PS, PS, PREC == 1 ? 1 : 2>;
+template <int NT, int CG, int PS, int PREC = 0, int STG = 0>
+using SplatFwdTc = SplatTcLayout<NT, CG, NT / CG, PS, PS, PREC == 1 ? 1 : 2, STG ? 16384 : 0>;
 
 // Work fused into the forward epilogue while the accumulator row sits in registers (the kernel is tensor-bound and
 // leaves HBM almost idle, so the HBM-bound passes of the loss block ride along for free):
@@ -273,11 +276,15 @@ struct FwdFuse {
 // 4 consecutive heliostats of the stage (one 16-byte chunk of the K-major row) and walks 8 of the
 // rows, so the footprint parameters sit in registers (loaded once per stage, prefetched one stage
 // ahead) and every warp store writes four full 128-byte rows of the swizzled tile, conflict-free.
-template <int NT, int CG, int PS, int FUSE, int PREC>
-__global__ void __launch_bounds__(SplatFwdTc<NT, CG, PS, PREC>::kThreads, 1)
+// STG = 1: the epilogue transposes each warp's 32 x 32 block through shared memory so that global stores are full 128-byte
+// row segments.  Measured on B200: -3...-12 % when the epilogue is a large share of the tile (few heliostats, and with the
+// f16x3 operands), +3...+5 % for large N under 3xTF32 (the staging competes with the operand traffic), so the launcher
+// picks it by N and operand format.
+template <int NT, int CG, int PS, int FUSE, int PREC, int STG>
+__global__ void __launch_bounds__(SplatFwdTc<NT, CG, PS, PREC, STG>::kThreads, 1)
 splat_fwd_tc_kernel(const float4* __restrict__ params, const int* __restrict__ counts, float* __restrict__ img, int N, int R,
                     Axis ax, Axis ay, int tiles_i, int tiles_j, int num_tiles, FwdFuse fz) {
-    using C = SplatFwdTc<NT, CG, PS, PREC>;
+    using C = SplatFwdTc<NT, CG, PS, PREC, STG>;
     extern __shared__ uint8_t smem_raw[];
     SplatTcCtx<C, CG> cx;
     cx.setup(smem_raw, R, ax, ay);
@@ -500,12 +507,33 @@ splat_fwd_tc_kernel(const float4* __restrict__ params, const int* __restrict__ c
 #pragma unroll
                     for (int e = 0; e < 32; ++e) v[e] *= 3.7252902984619140625e-09f;   // 2^-28, exact
                 }
-                if (i < R) {
-                    const bool full = vec && j0 + cb + 32 <= R;
-                    if (full) {
+                const bool full = vec && j0 + cb + 32 <= R;      // warp-uniform
+                if constexpr (STG == 1)
+                if (full) {
+                    // The accumulator arrives one image row per thread; storing it that way touches 32 cache lines per
+                    // instruction.  Transpose the warp's 32 x 32 block through shared memory (XOR-swizzled, conflict-free
+                    // both ways) so that every store instruction writes four full 128-byte row segments.
+                    const uint32_t stg = cx.epi_u + (uint32_t)q * 4096u;
+                    __syncwarp();                                // the previous block has been read out
 #pragma unroll
-                        for (int e = 0; e < 32; e += 4)
-                            *reinterpret_cast<float4*>(dst + cb + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+                    for (int c = 0; c < 8; ++c)
+                        tc::sts_v4(stg + (uint32_t)lane * 128u + ((uint32_t)(c ^ (lane & 7)) << 4), v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+                    __syncwarp();
+                    const int rrow = lane >> 3, ch = lane & 7;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const int row = 4 * k + rrow, gi = i0 + q * 32 + row;
+                        const float4 x = tc::lds_v4_volatile(stg + (uint32_t)row * 128u + ((uint32_t)(ch ^ (row & 7)) << 4));
+                        if (gi < R) *reinterpret_cast<float4*>(img + ((size_t)b * R + gi) * R + j0 + cb + 4 * ch) = x;
+                    }
+                }
+                if (i < R) {
+                    if (full) {
+                        if constexpr (STG == 0) {
+#pragma unroll
+                            for (int e = 0; e < 32; e += 4)
+                                *reinterpret_cast<float4*>(dst + cb + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+                        }
                     } else {
 #pragma unroll
                         for (int e = 0; e < 32; ++e)
@@ -597,10 +625,10 @@ inline int splat_tc_fwd_partials_per_image(int R, int num_sms, int pair) {
     return tiles * cg * 4;
 }
 
-template <int NT, int CG, int PS, int PREC = 0>
+template <int NT, int CG, int PS, int PREC = 0, int STG = 0>
 inline cudaError_t launch_splat_fwd_tc(const float* params, const int* counts, float* img, int B, int N, int R, float width,
                                        float height, int num_sms, cudaStream_t st, int fuse, const FwdFuse& fz) {
-    using C = SplatFwdTc<NT, CG, PS, PREC>;
+    using C = SplatFwdTc<NT, CG, PS, PREC, STG>;
     const int tiles_i = (R + C::kM * CG - 1) / (C::kM * CG), tiles_j = (R + NT - 1) / NT;
     const long long num_tiles = (long long)B * tiles_i * tiles_j;
     if (num_tiles > 0x7fffffffLL) return cudaErrorInvalidValue;
@@ -609,10 +637,14 @@ inline cudaError_t launch_splat_fwd_tc(const float* params, const int* counts, f
                                     reinterpret_cast<const float4*>(params), counts, img, N, R, make_axis(width, R),
                                     make_axis(height, R), tiles_i, tiles_j, (int)num_tiles, fz);
     };
-    if (fuse == kFuseMax) return go(splat_fwd_tc_kernel<NT, CG, PS, kFuseMax, PREC>);
-    if (fuse == kFuseLoss) return go(splat_fwd_tc_kernel<NT, CG, PS, kFuseLoss, PREC>);
-    return go(splat_fwd_tc_kernel<NT, CG, PS, kFuseNone, PREC>);
+    if (fuse == kFuseMax) return go(splat_fwd_tc_kernel<NT, CG, PS, kFuseMax, PREC, STG>);
+    if constexpr (STG == 0) {                        // the opt-in loss epilogue keeps the direct stores
+        if (fuse == kFuseLoss) return go(splat_fwd_tc_kernel<NT, CG, PS, kFuseLoss, PREC, 0>);
+    }
+    return go(splat_fwd_tc_kernel<NT, CG, PS, kFuseNone, PREC, STG>);
 }
+
+inline int sun_avg_k(int N) { return N; }   // contraction length a tile sees (culling only shortens it)
 
 // pair = 0: auto (CTA pairs for images taller than 128 rows), 1: single CTA, 2: CTA pairs
 // split = producer warps per 32-row operand slab (1 or 2; 0 = auto)
@@ -621,16 +653,24 @@ inline cudaError_t splat_tc_fwd(const float* params, float* img, int B, int N, i
                                 cudaStream_t st, int pair = 0, int split = 0, int fuse = kFuseNone, const FwdFuse& fz = FwdFuse{},
                                 const int* counts = nullptr, int prec = 0) {
 #define HELIO_FWD(NT_, CG_, PS_) launch_splat_fwd_tc<NT_, CG_, PS_>(params, counts, img, B, N, R, width, height, num_sms, st, fuse, fz)
+    // staged epilogue (see splat_fwd_tc_kernel): when the epilogue is a large share of a tile
+    const bool stg = fuse != kFuseLoss && split != 2 && (prec == 1 || sun_avg_k(N) < 1024);
     if (prec == 1) {                                 // opt-in f16x3 operands (see SplatFwdTc)
-#define HELIO_FWD16(NT_, CG_, PS_) launch_splat_fwd_tc<NT_, CG_, PS_, 1>(params, counts, img, B, N, R, width, height, num_sms, st, fuse, fz)
+#define HELIO_FWD16(NT_, CG_, PS_, STG_) launch_splat_fwd_tc<NT_, CG_, PS_, 1, STG_>(params, counts, img, B, N, R, width, height, num_sms, st, fuse, fz)
         if (R > 128) {
-            if (splat_tc_fwd_cg(R, num_sms, pair) == 2) return split == 2 ? HELIO_FWD16(256, 2, 2) : HELIO_FWD16(256, 2, 1);
-            return HELIO_FWD16(256, 1, 1);
+            if (splat_tc_fwd_cg(R, num_sms, pair) == 2) return split == 2 ? HELIO_FWD16(256, 2, 2, 0) : (stg ? HELIO_FWD16(256, 2, 1, 1) : HELIO_FWD16(256, 2, 1, 0));
+            return stg ? HELIO_FWD16(256, 1, 1, 1) : HELIO_FWD16(256, 1, 1, 0);
         }
-        if (R > 64) return split == 2 ? HELIO_FWD16(128, 1, 2) : HELIO_FWD16(128, 1, 1);
-        return HELIO_FWD16(64, 1, 1);
+        if (R > 64) return split == 2 ? HELIO_FWD16(128, 1, 2, 0) : (stg ? HELIO_FWD16(128, 1, 1, 1) : HELIO_FWD16(128, 1, 1, 0));
+        return stg ? HELIO_FWD16(64, 1, 1, 1) : HELIO_FWD16(64, 1, 1, 0);
 #undef HELIO_FWD16
     }
+#define HELIO_FWDS(NT_, CG_) launch_splat_fwd_tc<NT_, CG_, 1, 0, 1>(params, counts, img, B, N, R, width, height, num_sms, st, fuse, fz)
+    if (stg) {
+        if (R > 128) return splat_tc_fwd_cg(R, num_sms, pair) == 2 ? HELIO_FWDS(256, 2) : HELIO_FWDS(256, 1);
+        return R > 64 ? HELIO_FWDS(128, 1) : HELIO_FWDS(64, 1);
+    }
+#undef HELIO_FWDS
     if (R > 128) {
         if (splat_tc_fwd_cg(R, num_sms, pair) == 2) return split == 2 ? HELIO_FWD(256, 2, 2) : HELIO_FWD(256, 2, 1);
         return HELIO_FWD(256, 1, 1);

@@ -232,6 +232,13 @@ __device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
     lo = v - hi;
 }
 
+// shared-memory read that must not be hoisted or merged (staging buffers rewritten every iteration)
+__device__ __forceinline__ float4 lds_v4_volatile(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+
 // ---- packed fp32x2 arithmetic (sm_100: FADD2 / FMUL2 / FFMA2, two IEEE results per instruction) ------------
 struct f32x2 {
     unsigned long long r;
