@@ -461,7 +461,9 @@ def main_ours(args):
             ms_c = timed(lambda: one_step(action0), steps) / steps
             kc = Fn.collect_profile()
             Fn.reset_profile(False)
+            _g, _m = one_step(action0)                 # keep this step's graph alive: it owns the culled lists
             kept = Fn.last_cull_kept_fraction()
+            del _g, _m
             culled = dict(ms_per_step=ms_c, dense_equivalent_evals_per_s=evals_step / (ms_c * 1e-3), kept_fraction=kept,
                           kernels_ms={k: round(v["avg_ms"], 4) for k, v in sorted(kc.items())},
                           executed_tflops={k: FLOP_PER_EVAL[k] * float(B) * N * R * R * (kept if i else 0.5 * (1 + kept)) /

@@ -16,6 +16,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import weakref
 from typing import Optional
 
 import torch
@@ -275,7 +276,7 @@ def _cull_workspace(lib, B, N, dev):
     global _LAST_CULL
     nbytes = int(lib.helio_cull_workspace_bytes(B, N))
     ws = torch.empty((nbytes + 3) // 4, dtype=torch.int32, device=dev)
-    _LAST_CULL = (ws, B, N)
+    _LAST_CULL = (weakref.ref(ws), B, N)             # reporting only: must not keep the buffer alive
     return ws
 
 
@@ -283,7 +284,10 @@ def last_cull_kept_fraction():
     """Fraction of (sun, heliostat) pairs the most recent culled step kept (device sync; for reporting)."""
     if _LAST_CULL is None:
         return None
-    ws, B, N = _LAST_CULL
+    ref, B, N = _LAST_CULL
+    ws = ref()
+    if ws is None:
+        return None
     return float(ws[B * N * 5: B * N * 5 + B].sum().item()) / float(B * N)
 
 
