@@ -9,8 +9,8 @@
 //   columns: g[i][j]  = min_i' |i - i'| over mask pixels of column j (forward + backward scan, one thread per
 //            (b, j), coalesced over j), saturating at INF = 2R when the column has no mask pixel;
 //   rows   : d2[i][j] = min_j' (j - j')^2 + g[i][j']^2, one warp per image row with g^2 of the row in shared
-//            memory; each lane scans outwards from its pixel and stops once k^2 >= best (the scan length is the
-//            distance itself, neighbouring lanes stop together).
+//            memory; each lane scans outwards from its pixel in segments of 8 columns, skipping a segment whose
+//            lower bound (gap^2 + segment minimum) cannot improve the result and stopping once gap^2 >= best.
 // Everything is integer arithmetic, so the result is bit-identical to scipy's exact transform.  An image without
 // any mask pixel reproduces scipy's behaviour for an input without background (distance to a virtual pixel at
 // (-1, 0)); it only occurs for an all-zero image.
@@ -45,29 +45,63 @@ edt_cols_kernel(const float* __restrict__ img, const float* __restrict__ mx, flo
     }
 }
 
-// rows pass: one warp per (b, i)
+// rows pass: one warp per (b, i).  Exact minimisation of (j - j')^2 + g^2[j'] with two prunings that never drop the
+// minimiser: a direction stops once gap^2 >= best, and a segment of 8 columns is skipped when gap^2 + min(g^2 in the
+// segment) >= best.  Rows far from the mask (g^2 large and flat) finish after a few segment tests; rows through the mask
+// walk one segment minimum per 8 columns up to the distance itself.
+constexpr int kEdtSeg = 8;
+
 __global__ void __launch_bounds__(kEdtThreads)
 edt_rows_kernel(const short* __restrict__ g, int B, int R, float* __restrict__ dmaps) {
-    extern __shared__ int sG2[];                           // [warps][R]  g^2 of each warp's row
+    extern __shared__ int sEdt[];                          // [warps][R + nseg]  g^2 of each warp's row, then segment minima
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long row = (long long)blockIdx.x * (kEdtThreads / 32) + warp;
     if (row >= (long long)B * R) return;                   // whole warp leaves together
     const int i = (int)(row % R);
-    int* g2 = sG2 + warp * R;
+    const int nseg = (R + kEdtSeg - 1) / kEdtSeg;
+    int* g2 = sEdt + warp * (R + nseg);
+    int* seg = g2 + R;
     const short* src = g + (size_t)row * R;
     for (int j = lane; j < R; j += 32) {
         const int v = src[j];
         g2[j] = v * v;
     }
     __syncwarp();
+    for (int s = lane; s < nseg; s += 32) {
+        int m = 0x7fffffff;
+        for (int e = 0; e < kEdtSeg; ++e) {
+            const int jj = s * kEdtSeg + e;
+            if (jj < R) m = min(m, g2[jj]);
+        }
+        seg[s] = m;
+    }
+    __syncwarp();
     const int inf2 = 4 * R * R;
     float* dst = dmaps + (size_t)row * R;
     for (int j = lane; j < R; j += 32) {
         int best = g2[j];
-        for (int k = 1; k * k < best; ++k) {
-            const int kk = k * k;
-            if (j - k >= 0) best = min(best, g2[j - k] + kk);
-            if (j + k < R) best = min(best, g2[j + k] + kk);
+        const int js = j / kEdtSeg;
+        auto scan = [&](int s) {
+            for (int e = 0; e < kEdtSeg; ++e) {
+                const int jj = s * kEdtSeg + e;
+                if (jj < R) {
+                    const int d = jj - j;
+                    best = min(best, g2[jj] + d * d);
+                }
+            }
+        };
+        scan(js);
+        for (int s = js - 1; s >= 0; --s) {
+            const int gap = j - (s * kEdtSeg + kEdtSeg - 1);
+            const int gg = gap * gap;
+            if (gg >= best) break;
+            if (seg[s] + gg < best) scan(s);
+        }
+        for (int s = js + 1; s < nseg; ++s) {
+            const int gap = s * kEdtSeg - j;
+            const int gg = gap * gap;
+            if (gg >= best) break;
+            if (seg[s] + gg < best) scan(s);
         }
         if (best >= inf2) best = (i + 1) * (i + 1) + j * j;      // no mask pixel in the image: scipy's virtual pixel
         dst[j] = (float)sqrt((double)best);

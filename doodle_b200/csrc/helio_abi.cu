@@ -333,7 +333,7 @@ HELIO_API int helio_distance_maps(const float* img, int B, int R, float thr, flo
     {
         KernelTimer timer("edt_rows", stream);
         constexpr int warps = kEdtThreads / 32;
-        const size_t smem = (size_t)warps * R * sizeof(int);
+        const size_t smem = (size_t)warps * (R + (R + kEdtSeg - 1) / kEdtSeg) * sizeof(int);
         HELIO_CUDA_OK(cudaFuncSetAttribute(edt_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         edt_rows_kernel<<<(unsigned)(((long long)B * R + warps - 1) / warps), kEdtThreads, smem, st>>>(g, B, R, dmaps);
         HELIO_CUDA_OK(cudaGetLastError());
