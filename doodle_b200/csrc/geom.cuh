@@ -92,7 +92,8 @@ __device__ __forceinline__ float boundary_one(const Scene& sc, V3 h, V3 vct, V3*
     float xl = dot(local, sc.bu), yl = dot(local, sc.bv);
     float hw = sc.bw * tol / 2.f, hh = sc.bh * tol / 2.f;
     float ax = fabsf(xl) - hw * tol, ay = fabsf(yl) - hh * tol;
-    float dx = fmaxf(ax, 0.f), dy = fmaxf(ay, 0.f);
+    // F.relu propagates NaN (fmaxf would drop it): a NaN action must reach the NaN asserts of step (:495-501)
+    float dx = ax > 0.f ? ax : (ax != ax ? ax : 0.f), dy = ay > 0.f ? ay : (ay != ay ? ay : 0.f);
     float dist = sqrtf(dx * dx + dy * dy + 1e-8f);
     bool inside = (fabsf(xl) <= hw) && (fabsf(yl) <= hh) && valid;
     float outm = inside ? 0.f : 1.f;
@@ -114,7 +115,7 @@ __device__ __forceinline__ float boundary_one(const Scene& sc, V3 h, V3 vct, V3*
 __device__ __forceinline__ float angle_mrad(V3 ideal, V3 actual, float* g_dot) {
     const float hi = 0.99999994f, lo = -0.99999994f;
     float d = dot(ideal, actual);
-    float c = fminf(fmaxf(d, lo), hi);
+    float c = d != d ? d : fminf(fmaxf(d, lo), hi);    // torch.clamp propagates NaN
     if (g_dot) *g_dot = (d >= lo && d <= hi) ? -1000.f / sqrtf(1.f - c * c) : 0.f;
     return acosf(c) * 1000.f;
 }

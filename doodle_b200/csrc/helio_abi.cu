@@ -102,6 +102,13 @@ struct KernelTimer {
 
 inline unsigned geom_blocks(int B, int N) { return (unsigned)(((long long)B * N + kGeomThreads - 1) / kGeomThreads); }
 
+// tx[b] = floor: the fused per-image maximum (atomicMax on the int pattern of non-negative floats) then yields
+// max(max_ij target, floor) directly, the same clamped value helio_image_max returns (test_environment.py:436)
+__global__ void fill_kernel(float* __restrict__ p, int n, float v) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
 }  // namespace
 
 extern "C" {
@@ -440,8 +447,11 @@ HELIO_API int helio_step_fwd(const helio_scene_t* scene, const float* helio_pos,
     // target's per-image maximum, and the three per-image loss sums of the noisy image.
     const bool tc = splat_fwd_uses_tc(impl, B, N, R);
     const bool fused = loss_partials != nullptr && tc;   // loss sums in the noisy splat's epilogue
-    const char* fm = std::getenv("HELIO_FUSE_MAX");       // A/B switch (default on)
-    const bool fused_max = tc && !(fm && fm[0] == '0');  // target maximum in the target splat's epilogue
+    static const bool fuse_max_on = []() {                // A/B switch (default on), read once
+        const char* fm = std::getenv("HELIO_FUSE_MAX");
+        return !(fm && fm[0] == '0');
+    }();
+    const bool fused_max = tc && fuse_max_on;            // target maximum in the target splat's epilogue
     if (render_target) {
         // error-free field aimed with the ideal normals (test_environment.py:429-436).  It depends on the suns only,
         // so it goes first: a caller streaming the action in from the host overlaps that copy with these kernels.
@@ -449,9 +459,10 @@ HELIO_API int helio_step_fwd(const helio_scene_t* scene, const float* helio_pos,
         if (int rc = helio_geom_fwd(scene, helio_pos, sun, nullptr, nullptr, B, N, tgt_params, tgt_actual, tgt_refl, nullptr,
                                     nullptr, nullptr, nullptr, nullptr, 0, stream)) return rc;
         if (fused_max) {
-            HELIO_CUDA_OK(cudaMemsetAsync(tx, 0, (size_t)B * sizeof(float), (cudaStream_t)stream));
+            fill_kernel<<<(B + 255) / 256, 256, 0, (cudaStream_t)stream>>>(tx, B, 1e-6f);   // tx leaves this call clamped on every path
+            HELIO_CUDA_OK(cudaGetLastError());
             FwdFuse fz{};
-            fz.tile_max = tx;        // consumers clamp at 1e-6 (test_environment.py:436)
+            fz.tile_max = tx;
             if (int rc = splat_fwd_impl(tgt_params, B, N, R, scene->width, scene->height, target, impl, stream, kFuseMax, fz)) return rc;
         } else {
             if (int rc = helio_splat_fwd(tgt_params, B, N, R, scene->width, scene->height, target, impl, stream)) return rc;

@@ -71,20 +71,47 @@ def global_quantile(local_values: torch.Tensor, q: float, group=None) -> torch.T
     return torch.quantile(all_gather_cat(local_values, group), q)
 
 
+def sharded_randn(shard: Optional[Tuple[int, int, int]], batch: int, *tail: int, device=None) -> torch.Tensor:
+    """``torch.randn(batch, *tail)`` for a batch-leading tensor of a sharded environment.
+
+    ``shard = (global_batch, lo, hi)``: when ``batch`` is this rank's slice size the GLOBAL tensor
+    ``[global_batch, *tail]`` is drawn and rows ``[lo:hi]`` are kept, so that identically seeded ranks (a) hold disjoint
+    slices of one global draw -- not W copies of the same local draw -- and (b) leave the generator in the state the
+    single-process environment leaves it in (a CUDA ``randn`` cannot be sliced by skipping ahead: which Philox counter
+    feeds which element depends on the launch grid, i.e. on the total element count).  ``shard=None`` is a plain draw."""
+    if shard is not None and batch == shard[2] - shard[1]:
+        return torch.randn(shard[0], *tail, device=device)[shard[1]:shard[2]].contiguous()
+    return torch.randn(batch, *tail, device=device)
+
+
+def all_reduce_minmax(mn: torch.Tensor, mx: torch.Tensor, group=None):
+    """Global (min, max) of rank-local extrema (HelioEnv.ref_min / ref_max, test_environment.py:369-370)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return mn, mx
+    mn, mx = mn.detach().clone(), mx.detach().clone()
+    dist.all_reduce(mn, op=dist.ReduceOp.MIN, group=group)
+    dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=group)
+    return mn, mx
+
+
 def make_sharded_env(env_cls, *args, global_batch_size: int, rank: Optional[int] = None,
                      world_size: Optional[int] = None, group=None, seed: Optional[int] = None, **kwargs):
     """Build the rank-local slice of a ``global_batch_size`` HelioEnv.
 
-    All ranks seed identically, sample the GLOBAL sun batch and error tensors, then keep their slice,
-    so that concatenating the ranks reproduces the single-process environment exactly.  Metrics
-    returned by ``step`` are the global means; gradients w.r.t. the local actions are those of the
-    global means.
+    All ranks seed identically (``seed=`` or the caller's ``torch.manual_seed``) and every random tensor with a leading
+    batch dimension -- sun directions, ``batch_error_angles_mrad`` (constructor and every ``reset_errors``), the
+    ``init_actions`` noise -- is drawn at the GLOBAL batch size and sliced ``[lo:hi]`` (``sharded_randn``), so that
+    concatenating the ranks reproduces the single-process environment exactly, draw for draw.  ``ref_min`` / ``ref_max``
+    are all-reduced (min / max) in ``set_sun_pos``.  Metrics returned by ``step`` are the global means (one packed
+    all-reduce); gradients w.r.t. the local actions are those of the global means.
     """
     rank = dist.get_rank(group) if rank is None else rank
     world_size = dist.get_world_size(group) if world_size is None else world_size
     lo, hi = shard_bounds(global_batch_size, rank, world_size)
 
     class ShardedEnv(env_cls):  # type: ignore[misc, valid-type]
+        _batch_shard = (global_batch_size, lo, hi)       # read by HelioEnv.__init__ -> HelioField(batch_shard=...)
+
         def _sample_sun_pos(self):
             # draw the global batch with the local batch size temporarily widened
             local = self.batch_size
@@ -100,6 +127,9 @@ def make_sharded_env(env_cls, *args, global_batch_size: int, rank: Optional[int]
 
         def _quantile_cutoff(self, avg):
             return global_quantile(avg, 1 - self.error_mask_ratio, group)
+
+        def _reduce_minmax(self, mn, mx):
+            return all_reduce_minmax(mn, mx, group)
 
     if seed is not None:
         torch.manual_seed(seed)

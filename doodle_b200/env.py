@@ -15,15 +15,23 @@ Differences, all opt-in or bug-compatible:
     error-mask and exponential-risk variants are formed from its per-image sums / per-heliostat bounds;
   * a HOST action (CPU tensor or np.ndarray, which the reference accepts too, :411-412) is copied in on a side
     stream while the target renders, and its gradient is returned in pinned host memory, copied out slice by slice
-    under the backward kernels (functional.HostStepFn); ``obs['aux']`` is then built from the device copy (no
-    autograd link to the host action);
+    under the backward kernels (functional.HostStepFn); ``obs['aux']`` and ``monitor['normals']`` are then built from
+    the device copy, which HostStepFn returns as a differentiable output (gradients through them reach the host action);
   * ``cull`` (keyword-only, default False): the fused step contracts only over the heliostats whose footprint can
     reach the receiver (helio_cull: every dropped term is below 2^-40 of its peak on every pixel), which is most of the
     speed-up available when orientation errors are large; dense evaluation of every term, as in the reference, is the
     default;
-  * ``cache_target`` (keyword-only extension, default False = re-render the target every step as
-    the reference does, test_environment.py:429-435).  The target only depends on ``sun_pos``, so
-    caching it is exact.
+  * ``graph`` (keyword-only, default "auto"): for small fields -- where a step is launch + Python overhead, not kernel
+    time -- ``step`` replays captured CUDA graphs of the same fused forward / backward (graphs.StepGraph), transparently:
+    metrics keep their autograd history, the caller's ``loss.backward()`` works, several steps may be alive at once.
+    "auto" starts after two eager steps of a small shape (B*N*R^2 <= 2^33) on a device action without error mask,
+    exponential risk, culling or sharding; True drops the size limit; False never replays.  Results are bit-identical.
+    In graph mode the NaN/Inf asserts of step t are raised at the start of the next step / reset (no sync per step);
+  * ``cache_target`` (keyword-only extension, default True).  The reference re-renders the target of the
+    error-free field every step (test_environment.py:429-435) although it depends on ``sun_pos`` only; the
+    cached image is bit-identical to the re-rendered one.  The cache is keyed on the ``sun_pos`` tensor's
+    storage and version counter, so ``set_sun_pos`` AND in-place edits of ``env.sun_pos`` both invalidate it;
+    ``cache_target=False`` restores the per-step target render.
 """
 from __future__ import annotations
 
@@ -38,6 +46,7 @@ from scipy.ndimage import distance_transform_edt
 from .field import HelioField
 from .functional import HostStepFn, ImageLossFn, StepFn, _cf, image_max, require_cuda
 from .functional import distance_maps as _distance_maps_cuda
+from .graphs import GraphStepFn, StepGraph
 
 try:  # gymnasium is optional: only Env / spaces.Box / spaces.Dict are touched (test_environment.py:11-12)
     import gymnasium as gym
@@ -139,11 +148,12 @@ class HelioEnv(_EnvBase):
                  azimuth=45.0,
                  elevation=45.0,
                  *,
-                 cache_target=False,
+                 cache_target=True,
                  check_finite=True,
                  fused_step=True,
                  distance_maps_impl="auto",
                  cull=False,
+                 graph="auto",
                  ):
         super().__init__()
         require_cuda(torch.device(device), "HelioEnv")
@@ -182,6 +192,11 @@ class HelioEnv(_EnvBase):
         self._copy_stream = None
         self.distance_maps_impl = distance_maps_impl   # "auto"/"cuda": GPU EDT; "scipy": the reference's host path
         self._target_cache = None
+        if graph not in (True, False, "auto"):
+            raise ValueError(f"graph must be True, False or 'auto' (got {graph!r})")
+        self.graph = graph                             # transparent CUDA-graph replay of step (graphs.StepGraph)
+        self._step_graph = None
+        self._graph_warm = 0
 
         action_dim = heliostat_pos.shape[0] * 3
         self.action_space = spaces.Box(low=-1.0, high=1.0, shape=(action_dim,), dtype=np.float32)
@@ -194,7 +209,8 @@ class HelioEnv(_EnvBase):
         # two fields, same order as the reference so that seeded error draws line up (:255-277)
         common = dict(heliostat_positions=self.heliostat_pos, target_position=self.targ_pos, target_area=self.targ_area,
                       target_normal=self.targ_norm, sigma_scale=self.sigma_scale, resolution=self.resolution,
-                      max_batch_size=self.batch_size, device=self.device)
+                      max_batch_size=self.batch_size, device=self.device,
+                      batch_shard=getattr(self, "_batch_shard", None))   # set by dist.make_sharded_env: global draws, sliced
         self.ref_field = HelioField(error_scale_mrad=0.0, **common)
         self.noisy_field = HelioField(error_scale_mrad=self.error_scale_mrad, **common)
         for f in (self.ref_field, self.noisy_field):
@@ -239,6 +255,7 @@ class HelioEnv(_EnvBase):
 
     def set_sun_pos(self, sun_positions: torch.Tensor):
         """Fix the current sun positions and rebuild target-dependent state (:359-370)."""
+        self._check_deferred()
         self.sun_pos = sun_positions.clone().detach().to(device=self.device, dtype=torch.float32)
         self._target_cache = None
         self.ref_field.init_actions(self.sun_pos)
@@ -246,12 +263,12 @@ class HelioEnv(_EnvBase):
             ideal_normals = self.ref_field.calculate_ideal_normals(self.sun_pos)
             timg, _ = self.ref_field.render(self.sun_pos, self.ref_field.initial_action, ideal_normals)
         self.distance_maps = make_distance_maps(timg, impl=self.distance_maps_impl)
-        self.ref_min = torch.min(timg)
-        self.ref_max = torch.max(timg)
+        self.ref_min, self.ref_max = self._reduce_minmax(torch.min(timg), torch.max(timg))
 
     # ------------------------------------------------------------------ reset / step
     def reset(self):
         """Returns {'img': [B,R,R], 'aux': [B,3+3N] = cat(sun_pos, ideal normals)} (:372-400)."""
+        self._check_deferred()
         if self.new_sun_pos_every_reset:
             self.set_sun_pos(self._sample_sun_pos())
         if self.new_errors_every_reset:
@@ -263,28 +280,93 @@ class HelioEnv(_EnvBase):
         aux = torch.cat([self.sun_pos, out.ideal.flatten(1)], dim=1)
         return {'img': out.img, 'aux': aux}
 
+    # ---- exact target cache: (target, tx) depend on sun_pos only (:429-436) --------------------------------------
+    def _cache_key(self):
+        sp = self.sun_pos
+        return (sp.data_ptr(), sp._version, self.ref_field.splat_impl)
+
+    def _cached_target(self):
+        """(target, tx) of the current suns or (None, None); an in-place edit of ``sun_pos`` bumps its version counter
+        and a replaced tensor has another address, so a stale image is never returned."""
+        c = self._target_cache
+        if self.cache_target and c is not None and c[0] == self._cache_key():
+            return c[1], c[2]
+        return None, None
+
+    def _store_target(self, target, tx):
+        if self.cache_target:
+            self._target_cache = (self._cache_key(), target, tx)
+
     def _target(self, ideal: torch.Tensor):
         """Target image of the error-free field and its per-image max (:429-436)."""
-        if self.cache_target and self._target_cache is not None:
-            return self._target_cache
+        target, tx = self._cached_target()
+        if target is not None:
+            return target, tx
         with torch.no_grad():
             target = self.ref_field._render_full(self.sun_pos, ideal, want_aux=False).img
             tx = image_max(target)
-        if self.cache_target:
-            self._target_cache = (target, tx)
+        self._store_target(target, tx)
         return target, tx
 
     def _quantile_cutoff(self, avg_error_per_heatmap: torch.Tensor) -> torch.Tensor:
         """Global quantile over the batch (:445); the sharded env overrides this with an all-gather."""
         return torch.quantile(avg_error_per_heatmap, 1 - self.error_mask_ratio)
 
+    def _reduce_minmax(self, mn: torch.Tensor, mx: torch.Tensor):
+        """ref_min / ref_max of the target images (:369-370); the sharded env all-reduces (min, max) here."""
+        return mn, mx
+
     def _reduce_means(self, sums: torch.Tensor) -> torch.Tensor:
         """Packed {sum sq, sum dist, sum bound, sum angle} -> the four means (:128,455-457); the sharded
         env all-reduces here."""
         return sums * self._inv_counts
 
+    # ---- transparent CUDA-graph replay (graphs.StepGraph) ---------------------------------------------------------
+    def _check_deferred(self):
+        """Graph mode raises the NaN/Inf asserts of step t here, at the next entry into the env (:495-501)."""
+        sg = getattr(self, "_step_graph", None)
+        if sg is not None:
+            sg.check_pending()
+
+    def _graph_eligible(self, action) -> bool:
+        if self.graph is False or not self.fused_step or self.cull or self.use_error_mask or self.exponential_risk:
+            return False
+        if not (isinstance(action, torch.Tensor) and action.is_cuda):
+            return False
+        cls = type(self)
+        if cls._reduce_means is not HelioEnv._reduce_means or cls._quantile_cutoff is not HelioEnv._quantile_cutoff:
+            return False                                # sharded env: the metric all-reduce is not part of the graph
+        if self.graph == "auto":
+            B, N, R = self.batch_size, self.num_heliostats, self.resolution
+            if B * N * R * R > (1 << 33) or B * R * R > (1 << 26):
+                return False                            # kernel time dominates: replay (and its arena clone) buys nothing
+            if self._graph_warm < 2:                    # two eager steps first: one-time setup, cached target
+                self._graph_warm += 1
+                return False
+        return not torch.cuda.is_current_stream_capturing()   # a caller capturing its own graph gets the eager kernels
+
+    def _graph_step(self, action):
+        nf = self.noisy_field
+        sg = self._step_graph
+        impl_bwd = nf.splat_impl if nf.splat_impl_bwd is None else nf.splat_impl_bwd
+        if sg is None or sg.impl != nf.splat_impl or sg.impl_bwd != impl_bwd or sg.scene is not nf.scene():
+            sg = self._step_graph = StepGraph(self)
+            sg.capture_forward()
+        B, N = self.batch_size, self.num_heliostats
+        if action.dim() not in (2, 3) or action.shape[0] != B or action.numel() != 3 * B * N:
+            action = action.reshape(B, N, 3)                     # raises on a wrong element count, like the reference's view
+        img, means, aux, refl, bounds, angles, mae, ideal = GraphStepFn.apply(action, sg)
+        mse, dist_l, bound, alignment_loss = means.unbind(0)
+        return ({'img': img, 'aux': aux},
+                {'mse': mse, 'dist': dist_l, 'bound': bound, 'alignment_loss': alignment_loss},
+                {'normals': action.view(B, -1, 3), 'reflected_rays': refl, 'ideal_normals': ideal, 'all_bounds': bounds,
+                 'mae_image': mae, 'alignment_errors': angles})
+
     def step(self, action):
         """obs, metrics, monitor = step(action)   (:402-516).  action: [B, 3N] or [B, N, 3]."""
+        self._check_deferred()
+        if self._graph_eligible(action):
+            return self._graph_step(action)
         B, N, R = self.batch_size, self.num_heliostats, self.resolution
         fused = self.fused_step
         if isinstance(action, np.ndarray):                                           # :411-412
@@ -297,27 +379,27 @@ class HelioEnv(_EnvBase):
             # host-resident action: copies overlapped with the target render / the backward slices (HostStepFn)
             nf = self.noisy_field
             act = action if action.dtype == torch.float32 else action.float()
-            cached = self._target_cache if self.cache_target and self._target_cache is not None else (None, None)
+            cached = self._cached_target()
             if self._copy_stream is None:
                 self._copy_stream = torch.cuda.Stream(device=nf.device)
             img, packed, _actual, refl, ideal_normals, bounds, angles, per_img, target, tx, action_dev = HostStepFn.apply(
                 act.contiguous(), self.sun_pos, _cf(nf._select_errors(B)), nf.heliostat_positions, self.distance_maps, nf.scene(),
                 nf._geom_workspace(B), R, nf.splat_impl, nf.splat_impl if nf.splat_impl_bwd is None else nf.splat_impl_bwd,
                 cached[0], cached[1], self._copy_stream, self.host_chunks, self.cull)
-            if self.cache_target and self._target_cache is None:
-                self._target_cache = (target, tx)
+            if cached[0] is None:
+                self._store_target(target, tx)
             out = SimpleNamespace(refl=refl, bounds=bounds, angles=angles)
         elif fused:
             nf = self.noisy_field
             act = action.to(device=nf.device, dtype=torch.float32)
             normals = act.reshape(B, N, 3).contiguous()
-            cached = self._target_cache if self.cache_target and self._target_cache is not None else (None, None)
+            cached = self._cached_target()
             img, packed, _actual, refl, ideal_normals, bounds, angles, per_img, target, tx = StepFn.apply(
                 normals, self.sun_pos, _cf(nf._select_errors(B)), nf.heliostat_positions, self.distance_maps, nf.scene(),
                 nf._geom_workspace(B), R, nf.splat_impl, nf.splat_impl if nf.splat_impl_bwd is None else nf.splat_impl_bwd,
                 cached[0], cached[1], self.cull)
-            if self.cache_target and self._target_cache is None:
-                self._target_cache = (target, tx)
+            if cached[0] is None:
+                self._store_target(target, tx)
             out = SimpleNamespace(refl=refl, bounds=bounds, angles=angles)
         else:
             out = self.noisy_field._render_full(self.sun_pos, action, want_aux=True)     # K1 + K2
@@ -355,7 +437,7 @@ class HelioEnv(_EnvBase):
         metrics = {'mse': mse, 'dist': dist_l, 'bound': bound, 'alignment_loss': alignment_loss}
         obs = {'img': img, 'aux': aux}
         monitor = {
-            'normals': action.view(self.batch_size, -1, 3),
+            'normals': action_dev.view(self.batch_size, -1, 3),      # host action: its device copy (autograd-linked)
             'reflected_rays': out.refl.view([-1, 3]),
             'ideal_normals': ideal_normals.view([-1, 3]),
             'all_bounds': out.bounds,

@@ -12,7 +12,8 @@ from types import SimpleNamespace
 import torch
 
 from . import _lib
-from .functional import GeomFn, SplatFn, SPLAT_AUTO, Scene, _cf, require_cuda
+from .dist import sharded_randn
+from .functional import GeomFn, SplatFn, SPLAT_AUTO, Scene, _cf, _stream, require_cuda
 
 
 class HelioField:
@@ -30,7 +31,12 @@ class HelioField:
         resolution: int = 100,
         device: torch.device | str = "cpu",
         max_batch_size: int = 25,
+        *,
+        batch_shard=None,
     ) -> None:
+        # batch_shard (keyword-only extension, set by dist.make_sharded_env): (global_batch, lo, hi).  Random tensors with
+        # a leading batch dimension are then drawn for the GLOBAL batch and this rank's rows kept (dist.sharded_randn).
+        self.batch_shard = batch_shard
         self.device = torch.device(device)
         require_cuda(self.device, "HelioField")
         if self.device.index is None:
@@ -97,11 +103,15 @@ class HelioField:
         return self._scene
 
     def _geom_workspace(self, B: int) -> torch.Tensor:
-        ws = self._workspace.get(B)
+        """Ticket counter + block partials of K1's ordered reduction.  One workspace per (B, stream): two steps of the
+        same field enqueued on different streams must not share the counter (include/helio_b200.h: one stream per
+        workspace at a time)."""
+        key = (B, _stream())
+        ws = self._workspace.get(key)
         if ws is None:
             nbytes = _lib.load().helio_geom_workspace_bytes(B, self.num_heliostats)
             ws = torch.zeros((nbytes + 3) // 4, dtype=torch.int32, device=self.device)
-            self._workspace[B] = ws
+            self._workspace[key] = ws
         return ws
 
     # --------------------------------------------------------------------- API (reference :220-304)
@@ -117,7 +127,7 @@ class HelioField:
 
     def _sample_error_angles(self, batch_size: int) -> torch.Tensor:
         return (
-            torch.randn(batch_size, self.num_heliostats, 2, device=self.device)
+            sharded_randn(self.batch_shard, batch_size, self.num_heliostats, 2, device=self.device)
             * self.error_scale_mrad
         )
 
@@ -139,7 +149,10 @@ class HelioField:
     def init_actions(self, sun_position: torch.Tensor) -> None:
         """ideal + N(0, initial_action_noise), renormalised (:291-304)."""
         ideal = self.calculate_ideal_normals(sun_position)
-        noise = torch.randn_like(ideal) * self.initial_action_noise
+        if ideal.dim() == 3:
+            noise = sharded_randn(self.batch_shard, ideal.shape[0], self.num_heliostats, 3, device=self.device) * self.initial_action_noise
+        else:
+            noise = torch.randn_like(ideal) * self.initial_action_noise
         noisy = ideal + noise
         if ideal.dim() == 2:
             noisy = noisy / noisy.norm(dim=1, keepdim=True).clamp_min(1e-9)

@@ -246,9 +246,6 @@ class ImageLossFn(torch.autograd.Function):
         return g_img, None, None, None
 
 
-_PARTIALS_FLOATS = {}
-
-
 FUSE_LOSS_EPILOGUE = os.environ.get("HELIO_FUSE_LOSS", "0") == "1"
 
 
@@ -259,10 +256,7 @@ def _loss_partials(lib, B, N, R, impl, dev):
     The loss fusion is off by default: measured on B200 the fused epilogue's per-row loads of target / dmaps add ~20 %
     to the L1 data-pipe wavefronts that bound the forward splat (+0.8 ms at N=2000, R=256, B=4096) and save only the
     0.48 ms loss pass.  The per-image maximum of the target (no extra loads) is always fused on the tcgen05 path."""
-    key = (B, N, R, impl)
-    n = _PARTIALS_FLOATS.get(key)
-    if n is None:
-        n = _PARTIALS_FLOATS[key] = int(lib.helio_step_partials_floats(B, N, R, impl))
+    n = int(lib.helio_step_partials_floats(B, N, R, impl))     # cheap host call; depends on the run-time pair mode: not cached
     if not FUSE_LOSS_EPILOGUE or n == 0:
         return None, n > 0
     return torch.empty(n, dtype=torch.float32, device=dev), True
@@ -293,9 +287,9 @@ def last_cull_kept_fraction():
 
 def _step_fwd_kernels(render_target: bool, fused: bool, tc: bool = True) -> int:
     """Kernels helio_step_fwd enqueues: K1, K2, loss_pack (+ loss_fwd when the loss is not fused into K2's epilogue)
-    and, with the target render, K1, K2 (+ image_max on the CUDA-core path; the tcgen05 splat folds the maximum into
-    its epilogue; the memset is not counted)."""
-    return (3 if fused else 4) + ((2 if tc else 3) if render_target else 0)
+    and, with the target render, K1, K2 + either image_max (CUDA-core path) or the one-block fill of tx that seeds the
+    maximum folded into the tcgen05 splat's epilogue."""
+    return (3 if fused else 4) + (3 if render_target else 0)
 
 
 class StepFn(torch.autograd.Function):
@@ -375,9 +369,14 @@ class HostStepFn(torch.autograd.Function):
     test_environment.py:411-412), with the transfers overlapped instead of serialised:
 
       forward : the host->device copy of the action runs on a side stream while the main stream renders the target
-                (which depends on the suns only); the noisy render starts when the copy lands;
+                (which depends on the suns only); the noisy render starts when the copy lands.  With a cached target
+                there is nothing to hide under, so the copy and the forward both run in ``chunks`` slices of the sun
+                batch and slice k's kernels overlap slice k+1's copy;
       backward: runs in ``chunks`` slices of the sun batch; the device->host copy of a slice's action gradient
-                overlaps the next slice's kernels.  Returns the gradient as a pinned HOST tensor.
+                overlaps the next slice's kernels.  Returns the gradient as a HOST tensor, pinned when the input was.
+
+    The device copy of the action is returned as a differentiable output (obs['aux'] / monitor['normals'] are built from
+    it, test_environment.py:424,:505); a gradient arriving through it is added to the action gradient before it leaves.
 
     Same kernels, same numbers as StepFn (the per-sun slices are independent; packed sums are formed over the whole
     batch in the forward)."""
@@ -391,11 +390,6 @@ class HostStepFn(torch.autograd.Function):
         f32 = dict(dtype=torch.float32, device=dev)
         main = torch.cuda.current_stream(dev)
         action = torch.empty(B, N, 3, **f32)
-        copy_stream.wait_stream(main)                    # `action` is allocated on main's pool: order its first use
-        with torch.cuda.stream(copy_stream):
-            action.copy_(action_host.reshape(B, N, 3), non_blocking=True)
-            landed = torch.cuda.Event()
-            landed.record(copy_stream)
         params = torch.empty(B, N, 4, **f32)
         actual, refl, ideal_out = torch.empty(B, N, 3, **f32), torch.empty(B * N, 3, **f32), torch.empty(B, N, 3, **f32)
         bounds, angles = torch.empty(B, N, **f32), torch.empty(B, N, **f32)
@@ -404,10 +398,26 @@ class HostStepFn(torch.autograd.Function):
         global _LAUNCHES
         partials, tc = _loss_partials(lib, B, N, R, impl, dev)
         cull_ws = _cull_workspace(lib, B, N, dev) if cull and tc else None
-        if cull_ws is not None:
-            chunks = 1                                   # the culled lists are indexed by the whole batch
+        chunks = max(1, min(int(chunks), B))
+        if cull_ws is not None or partials is not None:
+            chunks = 1                                   # the culled lists / fused-loss partials are indexed by the whole batch
         render_target = target is None
+        # With the target to render the whole copy hides under it; with a cached target the forward itself runs in
+        # slices of the sun batch, each starting when its slice of the action has landed.
+        fwd_chunks = 1 if render_target else chunks
+        per = (B + fwd_chunks - 1) // fwd_chunks
+        landed = []
+        action_host3 = action_host.reshape(B, N, 3)
+        copy_stream.wait_stream(main)                    # `action` is allocated on main's pool: order its first use
+        with torch.cuda.stream(copy_stream):
+            for b0 in range(0, B, per):
+                nb = min(per, B - b0)
+                action.narrow(0, b0, nb).copy_(action_host3.narrow(0, b0, nb), non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+                landed.append(ev)
         nws = workspace.numel() * workspace.element_size()
+        sl = lambda t, b0, nb: None if t is None else t.narrow(0, b0, nb)
         with _Call("step_fwd_host", dev):
             if render_target:                            # phase 1, target only: it does not need the action
                 target, tx = torch.empty(B, R, R, **f32), torch.empty(B, **f32)
@@ -417,20 +427,40 @@ class HostStepFn(torch.autograd.Function):
                     None, _ptr(target), _ptr(tx), None, None, _ptr(scratch), _ptr(scratch[4 * B * N:]), _ptr(scratch[7 * B * N:]),
                     _ptr(partials), None, _ptr(workspace), nws, _stream())
                 _lib.check(rc, "helio_step_fwd (target)")
-            main.wait_event(landed)
-            rc = lib.helio_step_fwd(
-                C.byref(scene), _ptr(helio), _ptr(sun), _ptr(action), _ptr(errs), _ptr(dmaps), B, N, R, impl, 0,
-                _ptr(params), _ptr(actual), _ptr(refl), _ptr(ideal_out), _ptr(bounds), _ptr(angles), _ptr(img), _ptr(target),
-                _ptr(tx), _ptr(per_img), _ptr(packed), None, None, None, _ptr(partials), _ptr(cull_ws), _ptr(workspace), nws,
-                _stream())
-        _lib.check(rc, "helio_step_fwd")
+            if fwd_chunks == 1:
+                main.wait_event(landed[0])
+                rc = lib.helio_step_fwd(
+                    C.byref(scene), _ptr(helio), _ptr(sun), _ptr(action), _ptr(errs), _ptr(dmaps), B, N, R, impl, 0,
+                    _ptr(params), _ptr(actual), _ptr(refl), _ptr(ideal_out), _ptr(bounds), _ptr(angles), _ptr(img), _ptr(target),
+                    _ptr(tx), _ptr(per_img), _ptr(packed), None, None, None, _ptr(partials), _ptr(cull_ws), _ptr(workspace), nws,
+                    _stream())
+                _lib.check(rc, "helio_step_fwd")
+            else:
+                # per-slice forward; the per-image sums are the same numbers as in one call and are packed over the whole
+                # batch afterwards (bit-identical mse / dist); the bound / alignment sums are added slice by slice
+                parts = torch.empty(len(landed), 4, **f32)
+                refl3 = refl.view(B, N, 3)
+                for k, b0 in enumerate(range(0, B, per)):
+                    nb = min(per, B - b0)
+                    main.wait_event(landed[k])
+                    rc = lib.helio_step_fwd(
+                        C.byref(scene), _ptr(helio), _ptr(sl(sun, b0, nb)), _ptr(sl(action, b0, nb)), _ptr(sl(errs, b0, nb)),
+                        _ptr(sl(dmaps, b0, nb)), nb, N, R, impl, 0, _ptr(sl(params, b0, nb)), _ptr(sl(actual, b0, nb)),
+                        _ptr(sl(refl3, b0, nb)), _ptr(sl(ideal_out, b0, nb)), _ptr(sl(bounds, b0, nb)), _ptr(sl(angles, b0, nb)),
+                        _ptr(sl(img, b0, nb)), _ptr(sl(target, b0, nb)), _ptr(sl(tx, b0, nb)), _ptr(sl(per_img, b0, nb)), _ptr(parts[k]),
+                        None, None, None, None, None, _ptr(workspace), nws, _stream())
+                    _lib.check(rc, "helio_step_fwd (slice)")
+                    _LAUNCHES += _step_fwd_kernels(False, False, tc) if k else 0
+                _lib.check(lib.helio_loss_pack(_ptr(per_img), B, _ptr(packed), _stream()), "helio_loss_pack")
+                packed[2:].copy_(parts[:, 2:].sum(0))
+                _LAUNCHES += 1
         _LAUNCHES += _step_fwd_kernels(render_target, partials is not None, tc) - 1 + (1 if cull_ws is not None else 0)
         ctx.cull_ws = cull_ws
         ctx.save_for_backward(action, sun, errs, helio, dmaps, params, img, target, tx)
-        ctx.cfg = (scene, R, impl_bwd, copy_stream, max(1, min(int(chunks), B)), action_host.shape, action_host.is_pinned())
+        ctx.cfg = (scene, R, impl_bwd, copy_stream, chunks, action_host.shape, action_host.is_pinned())
         ctx.set_materialize_grads(False)
-        action_dev = action.view(B, N, 3)             # handed back (no gradient) so that obs['aux'] can be built on the device
-        ctx.mark_non_differentiable(ideal_out, target, tx, action_dev)
+        action_dev = action.view(B, N, 3)             # handed back so that obs['aux'] / monitor['normals'] live on the device
+        ctx.mark_non_differentiable(ideal_out, target, tx)
         return img, packed, actual, refl, ideal_out, bounds, angles, per_img, target, tx, action_dev
 
     @staticmethod
@@ -463,6 +493,8 @@ class HostStepFn(torch.autograd.Function):
                     _ptr(sl(g_img, b0, nb)), _ptr(sl(moments, b0, nb)), _ptr(sl(g_action, b0, nb)), _stream())
                 _lib.check(rc, "helio_step_bwd")
                 _LAUNCHES += (1 if need_img else 0) + (1 if need_splat else 0) + (1 if b0 else 0)
+                if g_adev is not None:                # gradient that arrived through the device copy (aux / monitor['normals'])
+                    g_action.narrow(0, b0, nb).add_(g_adev.reshape(B, N, 3).narrow(0, b0, nb))
                 done = torch.cuda.Event()
                 done.record(main)
                 with torch.cuda.stream(copy_stream):

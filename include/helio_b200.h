@@ -89,7 +89,9 @@ HELIO_API int helio_profile_count(void);
 HELIO_API int helio_profile_get(int index, const char** name, float* ms);
 
 /* Bytes of workspace helio_geom_fwd needs for (B, N) (block partials + ticket counter).  The
- * workspace must be zero-initialised ONCE by the caller; the kernel leaves it zeroed. */
+ * workspace must be zero-initialised ONCE by the caller; the kernel leaves it zeroed.  A workspace holds
+ * the ticket counter of the ordered reduction: use it from ONE stream at a time (one workspace per
+ * concurrently running call). */
 HELIO_API int64_t helio_geom_workspace_bytes(int B, int N);
 
 /* K1 forward.  Replaces, fused per (b, n):
@@ -220,7 +222,9 @@ HELIO_API int helio_loss_pack(const float* per_img, int B, float* packed, void* 
  * loss_partials (may be NULL): helio_step_partials_floats(B, N, R, impl) floats of scratch.  When given and
  * the shape takes the tcgen05 splat, image_max and loss_fwd do not run as separate passes: the target's
  * per-image maximum and the three per-image loss sums are accumulated in the splat epilogues while the
- * image rows are in registers (tx then holds the UNclamped maximum; every consumer clamps at 1e-6).
+ * image rows are in registers.  tx holds max(max_ij target, 1e-6) on every path (test_environment.py:436).
+ * A NaN pixel does not propagate into tx (fmaxf / integer max drop it; torch.amax would return NaN): the
+ * NaN then reaches the metrics through img / target themselves.
  *
  * cull_workspace (may be NULL = dense): helio_cull_workspace_bytes(B, N) bytes.  When given and the shape
  * takes the tcgen05 splat, the noisy render contracts only over the heliostats kept by helio_cull; pass

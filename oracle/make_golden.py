@@ -53,7 +53,7 @@ def npy(t):
 
 
 def render_case(ref_field, name, seed, N, R, B, helio_fn, sigma_scale, err_mrad, target_pos=(0., -5., 0.),
-                target_normal=(0., 1., 0.), area=(15., 15.), single=False, tweak=None, sun_fn=None):
+                target_normal=(0., 1., 0.), area=(15., 15.), single=False, tweak=None, sun_fn=None, w_seed=None):
     torch.manual_seed(seed)
     helio = helio_fn(N)
     field = ref_field.HelioField(helio, torch.tensor(target_pos), area, torch.tensor(target_normal),
@@ -74,7 +74,10 @@ def render_case(ref_field, name, seed, N, R, B, helio_fn, sigma_scale, err_mrad,
         action = tweak(action, field, sun)
     action = action.detach().requires_grad_(True)
     img, actual, refl = field.render(sun, action, ideal, monitor=True)
-    w_img = torch.randn_like(img)
+    # large cases: the image cotangent is regenerated from a frozen numpy stream instead of being stored
+    # (np.random.RandomState is guaranteed stable across numpy versions; tests/conftest.py::load_golden rebuilds it)
+    w_img = torch.randn_like(img) if w_seed is None else torch.from_numpy(
+        np.random.RandomState(w_seed).standard_normal(tuple(img.shape)).astype(np.float32))
     w_act = torch.randn_like(actual)
     w_ref = torch.randn_like(refl)
     g_img_only, = torch.autograd.grad((img * w_img).sum(), action, retain_graph=True)
@@ -87,7 +90,8 @@ def render_case(ref_field, name, seed, N, R, B, helio_fn, sigma_scale, err_mrad,
         area=np.asarray(area, np.float32), sigma_scale=np.float32(sigma_scale), err_mrad=np.float32(err_mrad),
         R=np.int32(R), single=np.bool_(single), sun=npy(sun), action=npy(action), errs=npy(errs), ideal=npy(ideal),
         error_angles_mrad=npy(field.error_angles_mrad), batch_error_angles_mrad=npy(field.batch_error_angles_mrad),
-        img=npy(img), actual=npy(actual), refl=npy(refl), w_img=npy(w_img), w_act=npy(w_act), w_ref=npy(w_ref),
+        img=npy(img), actual=npy(actual), refl=npy(refl),
+        **(dict(w_img=npy(w_img)) if w_seed is None else dict(w_seed=np.int64(w_seed))), w_act=npy(w_act), w_ref=npy(w_ref),
         grad_img_only=npy(g_img_only), grad_all=npy(g_all), plane_u=npy(field.plane_u), plane_v=npy(field.plane_v),
         target_normal_unit=npy(field.target_normal))
     print(f"render_{name}: img max {float(img.max()):.4f} |grad| {float(g_all.abs().max()):.3e}")
@@ -214,6 +218,16 @@ def main():
     env_case(ref_env, "exprisk", 24, N=5, R=16, B=3, sigma_scale=0.1, err_mrad=400.0, helio_fn=readme, exponential_risk=True)
     host_case(ref_env)
     com_case()
+
+    # ---- shapes that route to the tcgen05 kernels (R >= 48): the tensor-core path pinned on the reference itself ----
+    # BASELINE.json configs[0]/[1]: README quick start, N=50, 128x128, B=25, sigma_scale 0.1, 90 mrad
+    render_case(ref_field, "c1", 31, N=50, R=128, B=25, helio_fn=readme, sigma_scale=0.1, err_mrad=90.0, tweak=flip_one, w_seed=131)
+    # 256x256 receiver (BASELINE configs[3] resolution): NT=256 tiles, the CTA-pair (cta_group::2) kernels
+    render_case(ref_field, "r256", 32, N=64, R=256, B=2, helio_fn=trainer, sigma_scale=0.01, err_mrad=90.0, w_seed=132)
+    # 64x64: the NT=64 tile shape; N=130 spans two 128-heliostat blocks in the backward
+    render_case(ref_field, "r64", 33, N=130, R=64, B=3, helio_fn=trainer, sigma_scale=0.02, err_mrad=30.0, w_seed=133)
+    # BASELINE.json configs[1]: HelioEnv reset/step N=50, 128x128, B=25, new errors every reset, all four losses
+    env_case(ref_env, "c2", 34, N=50, R=128, B=25, sigma_scale=0.1, err_mrad=90.0, helio_fn=readme)
 
 
 if __name__ == "__main__":

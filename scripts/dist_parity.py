@@ -28,9 +28,16 @@ for (N, R, B, mask) in [(40, 64, 8 * world, False), (300, 256, 4 * world, False)
     full = HelioEnv(batch_size=B, **kw)                       # every rank also builds the global env (same seed)
     lo, hi = shard_bounds(B, rank, world)
     assert torch.equal(env.sun_pos, full.sun_pos[lo:hi])
-    # same errors and distance maps on both sides (reset draws depend on the batch size)
-    env.noisy_field.batch_error_angles_mrad = full.noisy_field.batch_error_angles_mrad[lo:hi].contiguous()
-    env.distance_maps = full.distance_maps[lo:hi].contiguous()
+    # nothing is copied in: the sharded env draws the GLOBAL error / init-noise tensors and keeps its rows, all-reduces
+    # ref_min / ref_max, and builds its distance maps from its own target images
+    assert torch.equal(env.noisy_field.batch_error_angles_mrad, full.noisy_field.batch_error_angles_mrad[lo:hi]), "constructor errors"
+    assert torch.equal(env.distance_maps, full.distance_maps[lo:hi]), "distance maps"
+    assert torch.equal(env.ref_min, full.ref_min) and torch.equal(env.ref_max, full.ref_max), "ref_min / ref_max"
+    torch.manual_seed(77); o_loc = env.reset()
+    torch.manual_seed(77); o_full = full.reset()
+    assert torch.equal(env.noisy_field.batch_error_angles_mrad, full.noisy_field.batch_error_angles_mrad[lo:hi]), "reset errors"
+    assert torch.equal(env.noisy_field.initial_action, full.noisy_field.initial_action[lo:hi]), "init_actions noise"
+    assert torch.equal(o_loc["img"], o_full["img"][lo:hi]), "reset image"
     torch.manual_seed(7)
     act_full = torch.nn.functional.normalize(full.ref_field.initial_action.view(B, N, 3) + 0.02 * torch.randn(B, N, 3, device=dev), dim=2)
     a_full = act_full.clone().requires_grad_(True)

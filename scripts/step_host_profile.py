@@ -9,7 +9,8 @@ torch.manual_seed(0)
 N, R, B = 50, 128, 25
 helio = torch.rand(N, 3, device=dev) * 10 + 80; helio[:, 2] = 0
 env = HelioEnv(helio, torch.tensor([0., -5., 0.], device=dev), (15., 15.), torch.tensor([0., 1., 0.], device=dev),
-               sigma_scale=0.1, error_scale_mrad=90.0, resolution=R, batch_size=B, device=dev, check_finite=False)
+               sigma_scale=0.1, error_scale_mrad=90.0, resolution=R, batch_size=B, device=dev,
+               graph=(False if "--eager" in sys.argv else "auto"))
 env.reset()
 a0 = env.ideal_normals.flatten(1).clone()
 def step(bwd=True):
@@ -19,6 +20,15 @@ def step(bwd=True):
         (m["mse"] + m["dist"] + m["bound"] + m["alignment_loss"]).backward()
 for _ in range(20): step()
 torch.cuda.synchronize()
+print("graph replay active:", env._step_graph is not None)
+def step_one_metric():
+    a = a0.detach().requires_grad_(True)
+    obs, m, mon = env.step(a)
+    m["dist"].backward()
+t0 = time.perf_counter()
+for _ in range(1000): step_one_metric()
+torch.cuda.synchronize()
+print(f"single-metric loss: {(time.perf_counter()-t0)*1e3:.1f} us/step wall")
 for bwd in (False, True):
     t0 = time.perf_counter()
     for _ in range(1000): step(bwd)

@@ -117,3 +117,74 @@ def test_make_sharded_env_slices_global_sun_batch():
         assert env.batch_size == 4 and env.sun_pos.shape == (4, 3)
         parts.append(env.sun_pos)
     assert torch.equal(torch.cat(parts), full)
+
+
+def test_sharded_randn_is_a_slice_of_the_global_draw():
+    """Identically seeded ranks must hold disjoint slices of ONE global draw (not W copies of a local draw) and leave
+    the generator where the single-process environment leaves it (dist.py seeded every rank identically and
+    drew local-sized error tensors)."""
+    from doodle_b200.dist import sharded_randn, shard_bounds
+    G, N, W = 12, 5, 3
+    torch.manual_seed(21)
+    full = torch.randn(G, N, 2)
+    after_full = torch.rand(4)
+    parts = []
+    for r in range(W):
+        lo, hi = shard_bounds(G, r, W)
+        torch.manual_seed(21)
+        parts.append(sharded_randn((G, lo, hi), hi - lo, N, 2))
+        assert torch.equal(torch.rand(4), after_full)            # generator state == single-process state
+    assert torch.equal(torch.cat(parts), full)
+    assert not torch.equal(parts[0], parts[1])                   # ranks differ
+    torch.manual_seed(21)
+    assert torch.equal(sharded_randn(None, G, N, 2), full)       # no shard: plain draw
+    torch.manual_seed(21)
+    assert sharded_randn((G, 0, 4), 1, N, 2).shape == (1, N, 2)  # not a batch-sized draw (B == 1 legacy errors): plain
+
+
+def _minmax_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from doodle_b200.dist import all_reduce_minmax
+    vals = torch.tensor([3.0, 7.0]) if rank == 0 else torch.tensor([-1.0, 5.0])
+    mn, mx = all_reduce_minmax(vals.min(), vals.max())
+    q.put((rank, float(mn), float(mx)))
+    dist.destroy_process_group()
+
+
+def test_ref_min_max_all_reduce():
+    """ref_min / ref_max (test_environment.py:369-370) must be the extrema over the GLOBAL batch on every rank."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_minmax_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for _, mn, mx in res:
+        assert (mn, mx) == (-1.0, 7.0)
+
+
+class _FakeField:
+    def __init__(self, batch_shard=None):
+        self.batch_shard = batch_shard
+
+
+class _FakeEnv2(_FakeEnv):
+    """Also exercises the hooks HelioEnv reads: the class-level _batch_shard and _reduce_minmax."""
+
+    def __init__(self, batch_size, **kw):
+        self.field = _FakeField(batch_shard=getattr(self, "_batch_shard", None))
+        super().__init__(batch_size, **kw)
+
+
+def test_make_sharded_env_passes_the_shard_to_the_fields():
+    from doodle_b200.dist import make_sharded_env
+    env = make_sharded_env(_FakeEnv2, global_batch_size=8, rank=1, world_size=2, seed=9)
+    assert env.field.batch_shard == (8, 4, 8)
+    mn, mx = env._reduce_minmax(torch.tensor(1.0), torch.tensor(2.0))     # no process group: identity
+    assert float(mn) == 1.0 and float(mx) == 2.0
