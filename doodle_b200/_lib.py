@@ -13,7 +13,7 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("HELIO_LIB_PATH") or os.path.join(_HERE, "libhelio_sm100.so")   # override: experiments only
 CSRC = os.path.join(_HERE, "csrc")
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 SPLAT_AUTO, SPLAT_SIMT, SPLAT_TC = 0, 1, 2
 
@@ -25,6 +25,7 @@ EXPORTS = (
     "helio_com_fwd", "helio_com_bwd",
     "helio_cull_workspace_bytes", "helio_cull", "helio_splat_fwd_culled", "helio_splat_bwd_culled",
     "helio_loss_bwd_packed", "helio_loss_pack", "helio_step_partials_floats", "helio_step_fwd", "helio_step_bwd",
+    "helio_splat_fwd_feed", "helio_step_fwd_feed",
 )
 
 
@@ -36,6 +37,12 @@ class Scene(C.Structure):
         ("bnd_targ_pos", C.c_float * 3), ("bnd_targ_norm", C.c_float * 3), ("bnd_u", C.c_float * 3),
         ("bnd_v", C.c_float * 3), ("bnd_width", C.c_float), ("bnd_height", C.c_float),
     ]
+
+
+class Feed(C.Structure):
+    """helio_feed_t (include/helio_b200.h): encoder-feed outputs of the splat epilogue."""
+    _fields_ = [("img2", C.c_void_p), ("img2_batch_stride", C.c_int64), ("eps", C.c_float), ("com_coords", C.c_void_p),
+                ("com_sums", C.c_void_p), ("partials", C.c_void_p)]
 
 
 class HelioLibError(RuntimeError):
@@ -113,6 +120,10 @@ def _declare(lib):
     lib.helio_loss_pack.argtypes = [p, i, p, p]
     lib.helio_step_fwd.restype = i
     lib.helio_step_fwd.argtypes = [sp, p, p, p, p, p, i, i, i, i, i] + [p] * 16 + [p, i64, p]
+    lib.helio_step_fwd_feed.restype = i
+    lib.helio_step_fwd_feed.argtypes = [sp, p, p, p, p, p, i, i, i, i, i] + [p] * 16 + [p, i64, C.POINTER(Feed), p]
+    lib.helio_splat_fwd_feed.restype = i
+    lib.helio_splat_fwd_feed.argtypes = [p, i, i, i, f, f, p, i, C.POINTER(Feed), p]
     lib.helio_step_partials_floats.restype = i64
     lib.helio_step_partials_floats.argtypes = [i, i, i, i]
     lib.helio_step_bwd.restype = i

@@ -269,6 +269,42 @@ HELIO_API int helio_splat_bwd(const float* params, const float* g_img, int B, in
     return splat_bwd_impl(params, g_img, B, N, R, width, height, moments, impl, stream);
 }
 
+namespace {
+// noisy splat with the encoder feed: fused into the tcgen05 epilogue, or (CUDA-core shapes) splat + helio_com_fwd + a strided copy
+int splat_fwd_feed_impl(const float* params, int B, int N, int R, float width, float height, float* img, int impl,
+                        const helio_feed_t* feed, void* stream, const int* counts = nullptr) {
+    HELIO_REQUIRE(feed != nullptr, "null pointer");
+    HELIO_REQUIRE((feed->com_coords == nullptr) == (feed->com_sums == nullptr), "com_coords and com_sums go together");
+    HELIO_REQUIRE(feed->img2 == nullptr || feed->img2_batch_stride >= (int64_t)R * R, "img2 batch stride smaller than an image");
+    const DeviceInfo* d = nullptr;
+    if (int rc = require_device(&d)) return rc;
+    if (splat_fwd_uses_tc(impl, B, N, R) && feed->partials != nullptr) {
+        FwdFuse fz{};
+        fz.partials = feed->partials, fz.img2 = feed->img2, fz.img2_bstride = (long long)feed->img2_batch_stride;
+        if (int rc = splat_fwd_impl(params, B, N, R, width, height, img, impl, stream, kFuseFeed, fz, counts)) return rc;
+        if (feed->com_coords) {
+            KernelTimer timer("com_pack", stream);
+            com_pack_partials_kernel<<<(B + kLossThreads - 1) / kLossThreads, kLossThreads, 0, (cudaStream_t)stream>>>(
+                feed->partials, splat_tc_fwd_partials_per_image(R, d->sms, tc_pair_mode()), B, feed->eps, feed->com_coords, feed->com_sums);
+            HELIO_CUDA_OK(cudaGetLastError());
+        }
+        return 0;
+    }
+    if (int rc = splat_fwd_impl(params, B, N, R, width, height, img, impl, stream, kFuseNone, FwdFuse{}, counts)) return rc;
+    if (feed->com_coords)
+        if (int rc = helio_com_fwd(img, B, R, R, feed->eps, feed->com_coords, feed->com_sums, stream)) return rc;
+    if (feed->img2)
+        HELIO_CUDA_OK(cudaMemcpy2DAsync(feed->img2, (size_t)feed->img2_batch_stride * 4, img, (size_t)R * R * 4, (size_t)R * R * 4, (size_t)B,
+                                        cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return 0;
+}
+}  // namespace
+
+HELIO_API int helio_splat_fwd_feed(const float* params, int B, int N, int R, float width, float height, float* img, int impl,
+                         const helio_feed_t* feed, void* stream) {
+    return splat_fwd_feed_impl(params, B, N, R, width, height, img, impl, feed, stream);
+}
+
 HELIO_API int64_t helio_cull_workspace_bytes(int B, int N) { return cull_workspace_bytes(B, N); }
 
 HELIO_API int helio_cull(const float* params, int B, int N, float width, float height, void* workspace, int64_t workspace_bytes,
@@ -437,6 +473,17 @@ HELIO_API int helio_step_fwd(const helio_scene_t* scene, const float* helio_pos,
                    float* actual, float* refl, float* ideal, float* bounds, float* angles, float* img, float* target,
                    float* tx, float* per_img, float* packed, float* tgt_params, float* tgt_actual, float* tgt_refl,
                    float* loss_partials, void* cull_workspace, void* workspace, int64_t workspace_bytes, void* stream) {
+    return helio_step_fwd_feed(scene, helio_pos, sun, action, errs, dmaps, B, N, R, impl, render_target, params, actual, refl, ideal,
+                               bounds, angles, img, target, tx, per_img, packed, tgt_params, tgt_actual, tgt_refl, loss_partials,
+                               cull_workspace, workspace, workspace_bytes, nullptr, stream);
+}
+
+HELIO_API int helio_step_fwd_feed(const helio_scene_t* scene, const float* helio_pos, const float* sun, const float* action,
+                        const float* errs, const float* dmaps, int B, int N, int R, int impl, int render_target, float* params,
+                        float* actual, float* refl, float* ideal, float* bounds, float* angles, float* img, float* target,
+                        float* tx, float* per_img, float* packed, float* tgt_params, float* tgt_actual, float* tgt_refl,
+                        float* loss_partials, void* cull_workspace, void* workspace, int64_t workspace_bytes,
+                        const helio_feed_t* feed, void* stream) {
     HELIO_REQUIRE(scene && target && tx, "null pointer");
     HELIO_REQUIRE(action == nullptr || (ideal && bounds && angles && img && per_img && packed && dmaps), "null pointer");
     HELIO_REQUIRE(action != nullptr || render_target, "nothing to do");
@@ -446,7 +493,7 @@ HELIO_API int helio_step_fwd(const helio_scene_t* scene, const float* helio_pos,
     // With the tensor-core splat the HBM-bound passes of the loss block ride in its epilogue (see FwdFuse): the
     // target's per-image maximum, and the three per-image loss sums of the noisy image.
     const bool tc = splat_fwd_uses_tc(impl, B, N, R);
-    const bool fused = loss_partials != nullptr && tc;   // loss sums in the noisy splat's epilogue
+    const bool fused = loss_partials != nullptr && tc && feed == nullptr;   // loss sums in the noisy splat's epilogue
     static const bool fuse_max_on = []() {                // A/B switch (default on), read once
         const char* fm = std::getenv("HELIO_FUSE_MAX");
         return !(fm && fm[0] == '0');
@@ -482,8 +529,11 @@ HELIO_API int helio_step_fwd(const helio_scene_t* scene, const float* helio_pos,
         sp = reinterpret_cast<const float*>(cb.cparams);
         counts = cb.counts;
     }
-    if (!fused)
+    if (feed) {
+        if (int rc = splat_fwd_feed_impl(sp, B, N, R, scene->width, scene->height, img, counts ? HELIO_SPLAT_TC : impl, feed, stream, counts)) return rc;
+    } else if (!fused) {
         if (int rc = splat_fwd_impl(sp, B, N, R, scene->width, scene->height, img, impl, stream, kFuseNone, FwdFuse{}, counts)) return rc;
+    }
     if (fused) {
         FwdFuse fz{};
         fz.target = target, fz.dmaps = dmaps, fz.tx = tx, fz.partials = loss_partials;

@@ -209,6 +209,22 @@ loss_pack_partials_kernel(const float* __restrict__ partials, int P, int B, floa
     }
 }
 
+// Feed epilogue (splat_tc.cuh, kFuseFeed): P partial records {sum w, sum w j, sum w i} per image -> com_sums[b][3] and
+// coords[b][2] exactly as com_fwd_kernel forms them (layers/center_of_mass.py:44-58).  Index order: deterministic.
+__global__ void __launch_bounds__(kLossThreads)
+com_pack_partials_kernel(const float* __restrict__ partials, int P, int B, float eps, float* __restrict__ coords,
+                         float* __restrict__ sums) {
+    const int b = blockIdx.x * kLossThreads + threadIdx.x;
+    if (b >= B) return;
+    const float* pp = partials + (size_t)b * P * 3;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+    for (int k = 0; k < P; ++k) s0 += __ldg(pp + 3 * k), s1 += __ldg(pp + 3 * k + 1), s2 += __ldg(pp + 3 * k + 2);
+    const bool mass = s0 > 0.f;
+    coords[2 * b] = mass ? s1 / (s0 + eps) : -1.f;
+    coords[2 * b + 1] = mass ? s2 / (s0 + eps) : -1.f;
+    if (sums) sums[3 * b] = s0, sums[3 * b + 1] = s1, sums[3 * b + 2] = s2;
+}
+
 // g_img = (2 g0 diff + (g1 dmaps + g2) sign(diff)) / tx (+ g_img_in); {g0,g1,g2} = g_per_img[b] (may be NULL) plus the
 // batch-wide {g_packed[0], g_packed[1], 0} (may be NULL): the adjoint of loss_pack_kernel folded in.
 __global__ void __launch_bounds__(kLossThreads)

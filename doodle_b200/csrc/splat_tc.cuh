@@ -263,13 +263,19 @@ using SplatFwdTc = SplatTcLayout<NT, CG, NT / CG, PS, PS, PREC == 1 ? 1 : 2, STG
 //   kFuseLoss: per-warp partials {sum diff^2, sum |diff| dmaps, sum |diff|}, diff = img/t - target/t, written to
 //              partials[b][tile][cta][warp][3] and combined in index order by loss_pack_partials_kernel, which
 //              replaces loss_fwd_kernel's pass over the image.
-enum : int { kFuseNone = 0, kFuseMax = 1, kFuseLoss = 2 };
+//   kFuseFeed: the encoder feed of the COM trainer (layers/center_of_mass.py:21-60, train_with_env.py:182-209): per-warp
+//              partials {sum w, sum w j, sum w i}, w = max(img, 0), combined in index order by com_pack_partials_kernel
+//              (replaces com_fwd_kernel's pass over the image), and an optional second copy of the image written
+//              straight into a caller-provided slot (e.g. hist[:, -1] of the rollout's history buffer).
+enum : int { kFuseNone = 0, kFuseMax = 1, kFuseLoss = 2, kFuseFeed = 3 };
 struct FwdFuse {
-    float* tile_max;         // [B]           kFuseMax (zero-initialised by the caller)
+    float* tile_max;         // [B]           kFuseMax (initialised to the floor by the caller)
     const float* target;     // [B][R][R]     kFuseLoss
     const float* dmaps;      // [B][R][R]
     const float* tx;         // [B]           (clamped to 1e-6 here)
-    float* partials;         // [B][tiles][CG][4][3]
+    float* partials;         // [B][tiles][CG][4][3]   kFuseLoss / kFuseFeed
+    float* img2;             // kFuseFeed: second destination of the image (may be NULL), image b at img2 + b * img2_bstride
+    long long img2_bstride;  //            in floats
 };
 
 // Producer mapping: a warp owns 32 operand rows (image rows for A, image columns for B); a lane owns
@@ -495,9 +501,29 @@ splat_fwd_tc_kernel(const float4* __restrict__ params, const int* __restrict__ c
             const int i = i0 + q * 32 + lane;
             const size_t row_off = ((size_t)b * R + i) * R + j0;
             float* dst = img + row_off;
+            // kFuseFeed: optional second copy of the image (e.g. the newest slot of a rollout's history buffer, batch stride given)
+            float* dst2 = nullptr;
+            if constexpr (FUSE == kFuseFeed) dst2 = fz.img2 ? fz.img2 + (size_t)b * fz.img2_bstride : nullptr;
             const uint32_t taddr = cx.tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * NT);
             const bool vec = (R & 3) == 0;
-            float f0 = 0.f, f1 = 0.f, f2 = 0.f;      // kFuseMax: f0 = running max; kFuseLoss: the three sums
+            // kFuseMax: f0 = running max; kFuseLoss: {sum diff^2, sum |diff| dmaps, sum |diff|}; kFuseFeed: {sum w, sum w j, sum w i}
+            float f0 = 0.f, f1 = 0.f, f2 = 0.f;
+            // one image element (value p at row gi, column gj) for the sums that ride in the epilogue; tq / dq = target / dmaps there
+            auto fuse_one = [&](float p, float tq, float dq, int gi, int gj) {
+                if constexpr (FUSE == kFuseLoss) {
+                    const float diff = p / tinv_t - tq / tinv_t;          // same arithmetic as loss_fwd_kernel
+                    const float ae = fabsf(diff);
+                    f0 = fmaf(diff, diff, f0);
+                    f1 = fmaf(ae, dq, f1);
+                    f2 += ae;
+                }
+                if constexpr (FUSE == kFuseFeed) {                        // CenterOfMass2D: w = max(x, 0), x = column, y = row
+                    const float w = fmaxf(p, 0.f);
+                    f0 += w;
+                    f1 = fmaf(w, (float)gj, f1);
+                    f2 = fmaf(w, (float)gi, f2);
+                }
+            };
 #pragma unroll 1
             for (int cb = 0; cb < NT; cb += 32) {
                 if (j0 + cb >= R) break;
@@ -512,7 +538,8 @@ splat_fwd_tc_kernel(const float4* __restrict__ params, const int* __restrict__ c
                 if (full) {
                     // The accumulator arrives one image row per thread; storing it that way touches 32 cache lines per
                     // instruction.  Transpose the warp's 32 x 32 block through shared memory (XOR-swizzled, conflict-free
-                    // both ways) so that every store instruction writes four full 128-byte row segments.
+                    // both ways) so that every store instruction writes four full 128-byte row segments -- and the loads of
+                    // target / dmaps for the fused loss sums are full row segments too.
                     const uint32_t stg = cx.epi_u + (uint32_t)q * 4096u;
                     __syncwarp();                                // the previous block has been read out
 #pragma unroll
@@ -520,11 +547,34 @@ splat_fwd_tc_kernel(const float4* __restrict__ params, const int* __restrict__ c
                         tc::sts_v4(stg + (uint32_t)lane * 128u + ((uint32_t)(c ^ (lane & 7)) << 4), v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
                     __syncwarp();
                     const int rrow = lane >> 3, ch = lane & 7;
+                    const int gj = j0 + cb + 4 * ch;
+                    float4 tq[8], dq[8];
+                    if constexpr (FUSE == kFuseLoss) {           // all 16 loads in flight before the first use
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            const int gi = i0 + q * 32 + 4 * k + rrow;
+                            const size_t o = ((size_t)b * R + min(gi, R - 1)) * R + gj;
+                            tq[k] = __ldg(reinterpret_cast<const float4*>(fz.target + o));
+                            dq[k] = __ldg(reinterpret_cast<const float4*>(fz.dmaps + o));
+                        }
+                    }
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
                         const int row = 4 * k + rrow, gi = i0 + q * 32 + row;
                         const float4 x = tc::lds_v4_volatile(stg + (uint32_t)row * 128u + ((uint32_t)(ch ^ (row & 7)) << 4));
-                        if (gi < R) *reinterpret_cast<float4*>(img + ((size_t)b * R + gi) * R + j0 + cb + 4 * ch) = x;
+                        if (gi < R) {
+                            *reinterpret_cast<float4*>(img + ((size_t)b * R + gi) * R + gj) = x;
+                            if constexpr (FUSE == kFuseFeed)
+                                if (dst2) *reinterpret_cast<float4*>(dst2 + (size_t)gi * R + gj) = x;
+                            if constexpr (FUSE == kFuseLoss) {
+                                fuse_one(x.x, tq[k].x, dq[k].x, gi, gj), fuse_one(x.y, tq[k].y, dq[k].y, gi, gj + 1);
+                                fuse_one(x.z, tq[k].z, dq[k].z, gi, gj + 2), fuse_one(x.w, tq[k].w, dq[k].w, gi, gj + 3);
+                            }
+                            if constexpr (FUSE == kFuseFeed) {
+                                fuse_one(x.x, 0.f, 0.f, gi, gj), fuse_one(x.y, 0.f, 0.f, gi, gj + 1);
+                                fuse_one(x.z, 0.f, 0.f, gi, gj + 2), fuse_one(x.w, 0.f, 0.f, gi, gj + 3);
+                            }
+                        }
                     }
                 }
                 if (i < R) {
@@ -533,39 +583,27 @@ splat_fwd_tc_kernel(const float4* __restrict__ params, const int* __restrict__ c
 #pragma unroll
                             for (int e = 0; e < 32; e += 4)
                                 *reinterpret_cast<float4*>(dst + cb + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+                            static_assert(FUSE == kFuseNone || FUSE == kFuseMax, "the loss / feed epilogues use the staged (coalesced) path");
                         }
                     } else {
+                        // ragged edge (R % 32 != 0 or R % 4 != 0): one image row per thread, scalar
+                        float* d2 = dst2 ? dst2 + (size_t)i * R + j0 : nullptr;
 #pragma unroll
                         for (int e = 0; e < 32; ++e)
-                            if (j0 + cb + e < R) dst[cb + e] = v[e];
+                            if (j0 + cb + e < R) {
+                                dst[cb + e] = v[e];
+                                if constexpr (FUSE == kFuseFeed) {
+                                    if (d2) d2[cb + e] = v[e];
+                                    fuse_one(v[e], 0.f, 0.f, i, j0 + cb + e);
+                                }
+                                if constexpr (FUSE == kFuseLoss)
+                                    fuse_one(v[e], __ldg(fz.target + row_off + cb + e), __ldg(fz.dmaps + row_off + cb + e), i, j0 + cb + e);
+                            }
                     }
                     if constexpr (FUSE == kFuseMax) {
 #pragma unroll
                         for (int e = 0; e < 32; ++e)
                             if (full || j0 + cb + e < R) f0 = fmaxf(f0, v[e]);
-                    }
-                    if constexpr (FUSE == kFuseLoss) {
-                        const float* tg = fz.target + row_off + cb;
-                        const float* dm = fz.dmaps + row_off + cb;
-                        auto one = [&](float p, float qv, float d) {
-                            const float diff = p / tinv_t - qv / tinv_t;      // same arithmetic as loss_fwd_kernel
-                            const float ae = fabsf(diff);
-                            f0 = fmaf(diff, diff, f0);
-                            f1 = fmaf(ae, d, f1);
-                            f2 += ae;
-                        };
-                        if (full) {
-#pragma unroll
-                            for (int e = 0; e < 32; e += 4) {
-                                const float4 tq = __ldg(reinterpret_cast<const float4*>(tg + e));
-                                const float4 dq = __ldg(reinterpret_cast<const float4*>(dm + e));
-                                one(v[e], tq.x, dq.x), one(v[e + 1], tq.y, dq.y), one(v[e + 2], tq.z, dq.z), one(v[e + 3], tq.w, dq.w);
-                            }
-                        } else {
-#pragma unroll
-                            for (int e = 0; e < 32; ++e)
-                                if (j0 + cb + e < R) one(v[e], __ldg(tg + e), __ldg(dm + e));
-                        }
                     }
                 }
             }
@@ -574,7 +612,7 @@ splat_fwd_tc_kernel(const float4* __restrict__ params, const int* __restrict__ c
                 f0 = warp_max(f0);
                 if (lane == 0) atomicMax(reinterpret_cast<int*>(fz.tile_max + b), __float_as_int(f0));
             }
-            if constexpr (FUSE == kFuseLoss) {
+            if constexpr (FUSE == kFuseLoss || FUSE == kFuseFeed) {
                 f0 = warp_sum(f0), f1 = warp_sum(f1), f2 = warp_sum(f2);
                 if (lane == 0) {
                     float* pp = fz.partials + ((((size_t)b * tiles_per_img + t) * CG + cx.rank) * 4 + q) * 3;
@@ -638,9 +676,11 @@ inline cudaError_t launch_splat_fwd_tc(const float* params, const int* counts, f
                                     make_axis(height, R), tiles_i, tiles_j, (int)num_tiles, fz);
     };
     if (fuse == kFuseMax) return go(splat_fwd_tc_kernel<NT, CG, PS, kFuseMax, PREC, STG>);
-    if constexpr (STG == 0) {                        // the opt-in loss epilogue keeps the direct stores
-        if (fuse == kFuseLoss) return go(splat_fwd_tc_kernel<NT, CG, PS, kFuseLoss, PREC, 0>);
+    if constexpr (STG == 1) {                        // the loss / feed epilogues work on the staged (coalesced) layout
+        if (fuse == kFuseLoss) return go(splat_fwd_tc_kernel<NT, CG, PS, kFuseLoss, PREC, 1>);
+        if (fuse == kFuseFeed) return go(splat_fwd_tc_kernel<NT, CG, PS, kFuseFeed, PREC, 1>);
     }
+    if (fuse == kFuseLoss || fuse == kFuseFeed) return cudaErrorInvalidValue;
     return go(splat_fwd_tc_kernel<NT, CG, PS, kFuseNone, PREC, STG>);
 }
 
@@ -654,7 +694,8 @@ inline cudaError_t splat_tc_fwd(const float* params, float* img, int B, int N, i
                                 const int* counts = nullptr, int prec = 0) {
 #define HELIO_FWD(NT_, CG_, PS_) launch_splat_fwd_tc<NT_, CG_, PS_>(params, counts, img, B, N, R, width, height, num_sms, st, fuse, fz)
     // staged epilogue (see splat_fwd_tc_kernel): when the epilogue is a large share of a tile
-    const bool stg = fuse != kFuseLoss && split != 2 && (prec == 1 || sun_avg_k(N) < 1024);
+    if (fuse == kFuseLoss || fuse == kFuseFeed) split = 1;      // those epilogues exist for the staged stores only
+    const bool stg = fuse == kFuseLoss || fuse == kFuseFeed || (split != 2 && (prec == 1 || sun_avg_k(N) < 1024));
     if (prec == 1) {                                 // opt-in f16x3 operands (see SplatFwdTc)
 #define HELIO_FWD16(NT_, CG_, PS_, STG_) launch_splat_fwd_tc<NT_, CG_, PS_, 1, STG_>(params, counts, img, B, N, R, width, height, num_sms, st, fuse, fz)
         if (R > 128) {

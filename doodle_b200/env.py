@@ -27,6 +27,12 @@ Differences, all opt-in or bug-compatible:
     "auto" starts after two eager steps of a small shape (B*N*R^2 <= 2^33) on a device action without error mask,
     exponential risk, culling or sharding; True drops the size limit; False never replays.  Results are bit-identical.
     In graph mode the NaN/Inf asserts of step t are raised at the start of the next step / reset (no sync per step);
+  * ``action_space="angular"`` (keyword-only): two angles per heliostat instead of a normal, the action space of the
+    reference's experimental newenv/test_environment_angular.py (``angles_to_normals``);
+  * encoder feed from the splat epilogue (keyword-only): ``HelioEnv(com=True)`` adds ``monitor['com']`` = the centre of
+    mass of every image (layers/center_of_mass.py:21-60), differentiable; ``step(action, img_out=hist[:, -1])`` also writes
+    the image straight into a caller's history slot (train_with_env.py:207-209).  Both come out of the kernel that renders
+    the image, not from extra passes over it;
   * ``cache_target`` (keyword-only extension, default True).  The reference re-renders the target of the
     error-free field every step (test_environment.py:429-435) although it depends on ``sun_pos`` only; the
     cached image is bit-identical to the re-rendered one.  The cache is keyed on the ``sun_pos`` tensor's
@@ -44,7 +50,7 @@ import torch.nn.functional as F
 from scipy.ndimage import distance_transform_edt
 
 from .field import HelioField
-from .functional import HostStepFn, ImageLossFn, StepFn, _cf, image_max, require_cuda
+from .functional import HostStepFn, ImageLossFn, StepFn, _cf, image_max, profiling, require_cuda
 from .functional import distance_maps as _distance_maps_cuda
 from .graphs import GraphStepFn, StepGraph
 
@@ -108,6 +114,18 @@ def sample_cone_directions(n: int, axis: torch.Tensor, half_angle_deg: float, de
     return dirs
 
 
+def angles_to_normals(action: torch.Tensor, num_heliostats: int) -> torch.Tensor:
+    """Angular action space of the reference's experimental env (newenv/test_environment_angular.py:205-214): two angles per
+    heliostat -> mirror normals [B,N,3], by rotating a north-pointing normal (0,1,0) with ``rotate_normals_batch``
+    (newenv_rl_test_multi_error.py:78-104): about Up by ``a[...,1]``, then about East by ``a[...,0]``.  As there, the
+    angles go through the rotation helper's mrad scaling (x 1e-3 rad).  Plain differentiable torch ops (a few tiny
+    kernels per step); the normals then enter the same fused step."""
+    a = action.reshape(action.shape[0], num_heliostats, 2)
+    e, u = a[..., 0] * 1e-3, a[..., 1] * 1e-3
+    cu = torch.cos(u)
+    return torch.stack([-torch.sin(u), torch.cos(e) * cu, torch.sin(e) * cu], dim=-1)
+
+
 def make_distance_maps(imgs: torch.Tensor, thr: float = 0.5, impl: str = "auto") -> torch.Tensor:
     """Per-image Euclidean distance to the >thr*max region (test_environment.py:92-97).
 
@@ -154,6 +172,8 @@ class HelioEnv(_EnvBase):
                  distance_maps_impl="auto",
                  cull=False,
                  graph="auto",
+                 action_space="normals",
+                 com=False,
                  ):
         super().__init__()
         require_cuda(torch.device(device), "HelioEnv")
@@ -194,11 +214,20 @@ class HelioEnv(_EnvBase):
         self._target_cache = None
         if graph not in (True, False, "auto"):
             raise ValueError(f"graph must be True, False or 'auto' (got {graph!r})")
+        # encoder feed: com=True adds monitor['com'] [B,2] = CenterOfMass2D(obs['img']) (differentiable),
+        # accumulated in the splat epilogue while the image tile is in registers (no extra pass over the image)
+        self.com = bool(com)
         self.graph = graph                             # transparent CUDA-graph replay of step (graphs.StepGraph)
         self._step_graph = None
         self._graph_warm = 0
 
-        action_dim = heliostat_pos.shape[0] * 3
+        if action_space not in ("normals", "angular"):
+            raise ValueError(f"action_space must be 'normals' or 'angular' (got {action_space!r})")
+        # "angular" (keyword-only extension): step takes two angles per heliostat, [B,2N] or [B,N,2], mapped to normals by
+        # angles_to_normals (the action space of newenv/test_environment_angular.py:110-111,205-214); everything after
+        # the mapping -- render, losses, monitors -- is the current env's step
+        self.action_kind = action_space
+        action_dim = heliostat_pos.shape[0] * (2 if action_space == "angular" else 3)
         self.action_space = spaces.Box(low=-1.0, high=1.0, shape=(action_dim,), dtype=np.float32)
         self.observation_space = spaces.Dict({
             'img': spaces.Box(low=0.0, high=np.inf, shape=(self.batch_size, resolution, resolution), dtype=np.float32),
@@ -329,7 +358,7 @@ class HelioEnv(_EnvBase):
             sg.check_pending()
 
     def _graph_eligible(self, action) -> bool:
-        if self.graph is False or not self.fused_step or self.cull or self.use_error_mask or self.exponential_risk:
+        if self.graph is False or not self.fused_step or self.cull or self.use_error_mask or self.exponential_risk or self.com:
             return False
         if not (isinstance(action, torch.Tensor) and action.is_cuda):
             return False
@@ -343,7 +372,8 @@ class HelioEnv(_EnvBase):
             if self._graph_warm < 2:                    # two eager steps first: one-time setup, cached target
                 self._graph_warm += 1
                 return False
-        return not torch.cuda.is_current_stream_capturing()   # a caller capturing its own graph gets the eager kernels
+        # a caller capturing its own graph, or timing kernels with helio_profile_*, gets the eager kernels
+        return not profiling() and not torch.cuda.is_current_stream_capturing()
 
     def _graph_step(self, action):
         nf = self.noisy_field
@@ -362,12 +392,21 @@ class HelioEnv(_EnvBase):
                 {'normals': action.view(B, -1, 3), 'reflected_rays': refl, 'ideal_normals': ideal, 'all_bounds': bounds,
                  'mae_image': mae, 'alignment_errors': angles})
 
-    def step(self, action):
-        """obs, metrics, monitor = step(action)   (:402-516).  action: [B, 3N] or [B, N, 3]."""
+    def step(self, action, *, img_out=None):
+        """obs, metrics, monitor = step(action)   (:402-516).  action: [B, 3N] or [B, N, 3].
+        ``img_out`` (keyword-only extension): a float32 [B,R,R] view (any batch stride) that also receives the image,
+        e.g. ``hist[:, -1]`` of the rollout's history buffer (train_with_env.py:207-209)."""
         self._check_deferred()
-        if self._graph_eligible(action):
+        if img_out is not None and not (self.fused_step and isinstance(action, torch.Tensor) and action.is_cuda):
+            raise ValueError("img_out needs the fused step and a device action")
+        if self.action_kind == "angular":
+            if isinstance(action, np.ndarray):
+                action = torch.from_numpy(np.ascontiguousarray(action, dtype=np.float32))
+            action = angles_to_normals(action.to(self.device), self.num_heliostats)
+        if img_out is None and self._graph_eligible(action):
             return self._graph_step(action)
         B, N, R = self.batch_size, self.num_heliostats, self.resolution
+        com = None
         fused = self.fused_step
         if isinstance(action, np.ndarray):                                           # :411-412
             action = torch.from_numpy(np.ascontiguousarray(action, dtype=np.float32))
@@ -394,10 +433,10 @@ class HelioEnv(_EnvBase):
             act = action.to(device=nf.device, dtype=torch.float32)
             normals = act.reshape(B, N, 3).contiguous()
             cached = self._cached_target()
-            img, packed, _actual, refl, ideal_normals, bounds, angles, per_img, target, tx = StepFn.apply(
+            img, packed, _actual, refl, ideal_normals, bounds, angles, per_img, target, tx, com, _com_sums = StepFn.apply(
                 normals, self.sun_pos, _cf(nf._select_errors(B)), nf.heliostat_positions, self.distance_maps, nf.scene(),
                 nf._geom_workspace(B), R, nf.splat_impl, nf.splat_impl if nf.splat_impl_bwd is None else nf.splat_impl_bwd,
-                cached[0], cached[1], self.cull)
+                cached[0], cached[1], self.cull, self.com, img_out)
             if cached[0] is None:
                 self._store_target(target, tx)
             out = SimpleNamespace(refl=refl, bounds=bounds, angles=angles)
@@ -444,6 +483,11 @@ class HelioEnv(_EnvBase):
             'mae_image': avg_error_per_heatmap.view([-1, 1]),
             'alignment_errors': out.angles.detach().view([-1]),
         }
+        if self.com:
+            if com is None:                     # host-action / composed routes: the layer's own kernel (one pass over the image)
+                from .layers import CenterOfMass2D
+                com = CenterOfMass2D()(img)
+            monitor['com'] = com
         return obs, metrics, monitor
 
     def seed(self, seed=None):

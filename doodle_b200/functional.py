@@ -22,7 +22,7 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import SPLAT_AUTO, SPLAT_SIMT, SPLAT_TC, Scene  # noqa: F401
+from ._lib import SPLAT_AUTO, SPLAT_SIMT, SPLAT_TC, Feed, Scene  # noqa: F401
 
 
 # ---- launch accounting / live per-kernel timing (bench.py reads these) ------------------------
@@ -34,9 +34,20 @@ def launch_count() -> int:
     return _LAUNCHES
 
 
+_PROFILE_ON = False
+
+
+def profiling() -> bool:
+    """True while helio_profile_enable(1) is in effect (event pairs cannot be recorded into a CUDA graph: HelioEnv then
+    keeps to the eager step)."""
+    return _PROFILE_ON
+
+
 def reset_profile(enabled: bool):
     """Switch the library's per-kernel CUDA-event timing on/off (helio_profile_enable); clears earlier records."""
+    global _PROFILE_ON
     _lib.check(_lib.load().helio_profile_enable(1 if enabled else 0), "helio_profile_enable")
+    _PROFILE_ON = bool(enabled)
 
 
 def collect_profile():
@@ -306,7 +317,11 @@ class StepFn(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, action, sun, errs, helio, dmaps, scene, workspace, R: int, impl: int, impl_bwd: int, target, tx, cull=False):
+    def forward(ctx, action, sun, errs, helio, dmaps, scene, workspace, R: int, impl: int, impl_bwd: int, target, tx, cull=False,
+                want_com=False, img_out=None):
+        """``want_com`` / ``img_out`` (encoder feed, helio_step_fwd_feed): the centre of mass of the noisy image and a second
+        copy of it in ``img_out`` ([B,R,R] view, any batch stride, contiguous images) come out of the splat epilogue; the
+        extra outputs com [B,2] (differentiable) and com_sums [B,3] are appended."""
         lib = _lib.load()
         B, N = sun.shape[0], helio.shape[0]
         dev = action.device
@@ -323,30 +338,59 @@ class StepFn(torch.autograd.Function):
             scratch = torch.empty(B * N * 10, **f32)     # params, actual, refl of the target render (discarded)
         partials, tc = _loss_partials(lib, B, N, R, impl, dev)
         cull_ws = _cull_workspace(lib, B, N, dev) if cull and tc else None
+        feed = com = com_sums = feed_partials = None
+        if want_com or img_out is not None:
+            feed = Feed()
+            feed.eps = 1e-12
+            if want_com:
+                com, com_sums = torch.empty(B, 2, **f32), torch.empty(B, 3, **f32)
+                feed.com_coords, feed.com_sums = com.data_ptr(), com_sums.data_ptr()
+            if img_out is not None:
+                if tuple(img_out.shape) != (B, R, R) or img_out.dtype != torch.float32 or img_out.device != dev or \
+                        img_out.stride(1) != R or img_out.stride(2) != 1:
+                    raise ValueError("img_out must be a float32 [B,R,R] view on the env's device with contiguous images")
+                feed.img2, feed.img2_batch_stride = img_out.data_ptr(), img_out.stride(0)
+            nfl = int(lib.helio_step_partials_floats(B, N, R, impl))
+            if nfl > 0:
+                feed_partials = torch.empty(nfl, **f32)
+                feed.partials = feed_partials.data_ptr()
         with _Call("step_fwd", dev):
-            rc = lib.helio_step_fwd(
+            rc = lib.helio_step_fwd_feed(
                 C.byref(scene), _ptr(helio), _ptr(sun), _ptr(action), _ptr(errs), _ptr(dmaps), B, N, R, impl,
                 1 if render_target else 0, _ptr(params), _ptr(actual), _ptr(refl), _ptr(ideal), _ptr(bounds), _ptr(angles),
                 _ptr(img), _ptr(target), _ptr(tx), _ptr(per_img), _ptr(packed),
                 _ptr(scratch), _ptr(scratch[4 * B * N:]) if render_target else None,
                 _ptr(scratch[7 * B * N:]) if render_target else None, _ptr(partials), _ptr(cull_ws),
-                _ptr(workspace), workspace.numel() * workspace.element_size(), _stream())
+                _ptr(workspace), workspace.numel() * workspace.element_size(), None if feed is None else C.byref(feed), _stream())
         _lib.check(rc, "helio_step_fwd")
         global _LAUNCHES
-        _LAUNCHES += _step_fwd_kernels(render_target, partials is not None, tc) - 1 + (1 if cull_ws is not None else 0)
-        ctx.save_for_backward(action, sun, errs, helio, dmaps, params, img, target, tx)
+        _LAUNCHES += _step_fwd_kernels(render_target, partials is not None and feed is None, tc) - 1 + (1 if cull_ws is not None else 0) \
+            + (1 if want_com else 0)
+        ctx.save_for_backward(action, sun, errs, helio, dmaps, params, img, target, tx, com_sums)
         ctx.cull_ws = cull_ws
         ctx.cfg = (scene, R, impl_bwd)
         ctx.set_materialize_grads(False)
         ctx.mark_non_differentiable(ideal, target, tx)
-        return img, packed, actual, refl, ideal, bounds, angles, per_img, target, tx
+        if want_com:
+            ctx.mark_non_differentiable(com_sums)
+        return img, packed, actual, refl, ideal, bounds, angles, per_img, target, tx, com, com_sums
 
     @staticmethod
-    def backward(ctx, g_img_in, g_packed, g_actual, g_refl, g_ideal, g_bounds, g_angles, g_per_img, g_target, g_tx):
+    def backward(ctx, g_img_in, g_packed, g_actual, g_refl, g_ideal, g_bounds, g_angles, g_per_img, g_target, g_tx, g_com=None,
+                 g_com_sums=None):
         lib = _lib.load()
-        action, sun, errs, helio, dmaps, params, img, target, tx = ctx.saved_tensors
+        action, sun, errs, helio, dmaps, params, img, target, tx, com_sums = ctx.saved_tensors
         scene, R, impl = ctx.cfg
         B, N = sun.shape[0], helio.shape[0]
+        global _LAUNCHES
+        if g_com is not None:
+            # adjoint of the centre of mass (helio_com_bwd): one elementwise pass producing dL/dimg, which joins whatever
+            # arrives through obs['img'] and enters the loss backward / K3 as g_img_in
+            g_img_com = torch.empty_like(img)
+            _lib.check(lib.helio_com_bwd(_ptr(img), _ptr(com_sums), _ptr(_cf(g_com)), B, R, R, 1e-12, _ptr(g_img_com), _stream()),
+                       "helio_com_bwd")
+            _LAUNCHES += 1
+            g_img_in = g_img_com if g_img_in is None else g_img_com.add_(g_img_in)
         gs = [None if g is None else _cf(g) for g in (g_packed, g_per_img, g_img_in, g_actual, g_refl, g_bounds, g_angles)]
         need_img = gs[0] is not None or gs[1] is not None
         need_splat = need_img or gs[2] is not None
@@ -359,9 +403,26 @@ class StepFn(torch.autograd.Function):
                 _ptr(dmaps), _ptr(tx), B, N, R, impl, *[_ptr(g) for g in gs], _ptr(ctx.cull_ws),
                 _ptr(g_img), _ptr(moments), _ptr(g_action), _stream())
         _lib.check(rc, "helio_step_bwd")
-        global _LAUNCHES
         _LAUNCHES += (1 if need_img else 0) + (1 if need_splat else 0)
-        return (g_action,) + (None,) * 12
+        return (g_action,) + (None,) * 14
+
+
+def _host_slices(B: int, chunks: int, small_first: bool):
+    """[(b0, nb)] slices of the sun batch for overlapping host copies with kernels.  The one copy that cannot hide -- the first
+    host->device slice of the forward, the last device->host slice of the backward -- is a quarter of the others."""
+    chunks = max(1, min(int(chunks), B))
+    if chunks == 1:
+        return [(0, B)]
+    small = max(1, int(round(0.25 * B / (chunks - 0.75))))
+    rest = B - small
+    sizes = [rest // (chunks - 1) + (1 if i < rest % (chunks - 1) else 0) for i in range(chunks - 1)]
+    sizes = [small] + sizes if small_first else sizes + [small]
+    out, b0 = [], 0
+    for nb in sizes:
+        if nb > 0:
+            out.append((b0, nb))
+            b0 += nb
+    return out
 
 
 class HostStepFn(torch.autograd.Function):
@@ -404,14 +465,13 @@ class HostStepFn(torch.autograd.Function):
         render_target = target is None
         # With the target to render the whole copy hides under it; with a cached target the forward itself runs in
         # slices of the sun batch, each starting when its slice of the action has landed.
-        fwd_chunks = 1 if render_target else chunks
-        per = (B + fwd_chunks - 1) // fwd_chunks
+        fwd_slices = _host_slices(B, 1 if render_target else chunks, small_first=True)
+        fwd_chunks = len(fwd_slices)
         landed = []
         action_host3 = action_host.reshape(B, N, 3)
         copy_stream.wait_stream(main)                    # `action` is allocated on main's pool: order its first use
         with torch.cuda.stream(copy_stream):
-            for b0 in range(0, B, per):
-                nb = min(per, B - b0)
+            for b0, nb in fwd_slices:
                 action.narrow(0, b0, nb).copy_(action_host3.narrow(0, b0, nb), non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(copy_stream)
@@ -440,8 +500,7 @@ class HostStepFn(torch.autograd.Function):
                 # batch afterwards (bit-identical mse / dist); the bound / alignment sums are added slice by slice
                 parts = torch.empty(len(landed), 4, **f32)
                 refl3 = refl.view(B, N, 3)
-                for k, b0 in enumerate(range(0, B, per)):
-                    nb = min(per, B - b0)
+                for k, (b0, nb) in enumerate(fwd_slices):
                     main.wait_event(landed[k])
                     rc = lib.helio_step_fwd(
                         C.byref(scene), _ptr(helio), _ptr(sl(sun, b0, nb)), _ptr(sl(action, b0, nb)), _ptr(sl(errs, b0, nb)),
@@ -476,14 +535,12 @@ class HostStepFn(torch.autograd.Function):
         g_action = torch.empty_like(action)
         g_img = torch.empty_like(img) if need_img else None
         moments = torch.empty_like(params) if need_splat else None
-        h_grad = torch.empty(B, N, 3, dtype=torch.float32, pin_memory=pinned)
+        h_grad = torch.empty(B, N, 3, dtype=torch.float32, device="cpu", pin_memory=pinned)   # explicit: callers may set a CUDA default device
         main = torch.cuda.current_stream(dev)
         sl = lambda t, b0, nb: None if t is None else t.narrow(0, b0, nb)
         global _LAUNCHES
-        per = (B + chunks - 1) // chunks
         with _Call("step_bwd_host", dev):
-            for b0 in range(0, B, per):
-                nb = min(per, B - b0)
+            for b0, nb in _host_slices(B, chunks, small_first=False):
                 refl_g = None if gs[4] is None else gs[4].view(B, N, 3).narrow(0, b0, nb)
                 rc = lib.helio_step_bwd(
                     C.byref(scene), _ptr(helio), _ptr(sl(sun, b0, nb)), _ptr(sl(action, b0, nb)), _ptr(sl(errs, b0, nb)),

@@ -95,7 +95,7 @@ class StepGraph:
         self._errs_src = None                                   # (tensor, version) of the error tensor last copied in
         # deferred finite check (test_environment.py:495-501): the three means land in pinned host memory through a
         # copy node of the forward graph and are examined at the start of the NEXT step -- no sync in the step itself
-        self.host_means = torch.zeros(4, dtype=torch.float32).pin_memory()
+        self.host_means = torch.zeros(4, dtype=torch.float32, device="cpu").pin_memory()   # explicit: callers may set a CUDA default device
         self.host_means_np = self.host_means.numpy()            # same memory; reading three floats costs no torch dispatch
         self.fwd_done = torch.cuda.Event()
         self._stream_obj, self._stream_raw = None, None         # torch Stream object of the raw handle last seen (building one costs ~20 us)

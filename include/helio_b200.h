@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define HELIO_ABI_VERSION 4
+#define HELIO_ABI_VERSION 5
 
 #if defined(__GNUC__)
 #define HELIO_API __attribute__((visibility("default")))
@@ -237,6 +237,39 @@ HELIO_API int helio_step_fwd(const helio_scene_t* scene_host, const float* helio
                    float* img, float* target, float* tx, float* per_img, float* packed,
                    float* tgt_params, float* tgt_actual, float* tgt_refl, float* loss_partials,
                    void* cull_workspace, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Encoder feed of the reference's rollout (train_with_env.py:182-209: hist[:, -1] = img, then the policy's encoder;
+ * train_with_env_com_trunc_advantage_ttt.py:42-53: CenterOfMass2D of every history frame, layers/center_of_mass.py:21-60)
+ * produced WHILE the image tile is still in the splat epilogue's registers, instead of by extra passes over the image:
+ *   com_coords[B][2], com_sums[B][3]  centre of mass of the noisy image exactly as helio_com_fwd returns it
+ *                                     (coords = (sum w j, sum w i) / (sum w + eps), w = max(img, 0); (-1,-1) without mass);
+ *   img2 (may be NULL)                a second copy of the image, image b at img2 + b * img2_batch_stride floats
+ *                                     (e.g. the newest slot of a [B][k][R][R] history buffer: stride k R R).
+ * partials: helio_step_partials_floats(B, N, R, impl) floats of scratch (0 floats = shape not on the tcgen05 path: the
+ * same results then come from helio_com_fwd and a strided copy, nothing is fused).  Plain host struct, passed by pointer. */
+typedef struct helio_feed {
+    float* img2;
+    int64_t img2_batch_stride;
+    float eps;              /* CenterOfMass2D.eps (1e-12) */
+    float* com_coords;      /* [B][2], may be NULL together with com_sums */
+    float* com_sums;        /* [B][3] */
+    float* partials;
+} helio_feed_t;
+
+/* helio_splat_fwd with the feed outputs (K2 + centre of mass + optional second image copy in one kernel). */
+HELIO_API int helio_splat_fwd_feed(const float* params, int B, int N, int R, float width, float height, float* img, int impl,
+                         const helio_feed_t* feed_host, void* stream);
+
+/* helio_step_fwd with the feed outputs taken from the noisy render's epilogue (all other arguments as helio_step_fwd;
+ * with feed_host != NULL the loss sums run as the separate loss_fwd pass: loss_partials is ignored). */
+HELIO_API int helio_step_fwd_feed(const helio_scene_t* scene_host, const float* helio, const float* sun,
+                        const float* action, const float* errs, const float* dmaps,
+                        int B, int N, int R, int impl, int render_target,
+                        float* params, float* actual, float* refl, float* ideal, float* bounds, float* angles,
+                        float* img, float* target, float* tx, float* per_img, float* packed,
+                        float* tgt_params, float* tgt_actual, float* tgt_refl, float* loss_partials,
+                        void* cull_workspace, void* workspace, int64_t workspace_bytes,
+                        const helio_feed_t* feed_host, void* stream);
 
 /* Backward of helio_step_fwd down to g_action[B][N][3]: K4' (g_img) -> K3 (moments) -> K1'.
  * g_packed[4] (device) = upstream grads of packed; g_per_img[B][3], g_img_in[B][R][R] (gradient

@@ -175,6 +175,21 @@ def com_case():
     print("com: ", out["sq_coords"][:3].tolist())
 
 
+def angular_case(ref_field):
+    """Angular action space (newenv/test_environment_angular.py:205-214): north-pointing normals rotated by the action's two
+    angles with the reference's rotate_normals_batch, plus autograd of a weighted sum."""
+    torch.manual_seed(41)
+    B, N = 3, 7
+    angles = (torch.randn(B, N * 2) * 400.0).requires_grad_(True)          # the helper scales by 1e-3: +-0.4 rad
+    north = torch.zeros(B * N, 3)
+    north[:, 1] = 1.0
+    normals = ref_field.rotate_normals_batch(north, angles.view(-1, 2)).view(B, N, 3)
+    w = torch.randn_like(normals)
+    g, = torch.autograd.grad((normals * w).sum(), angles)
+    np.savez_compressed(os.path.join(OUT, "angular.npz"), angles=npy(angles), normals=npy(normals), w=npy(w), grad=npy(g))
+    print("angular:", normals[0, 0].tolist())
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref_field, ref_env = import_reference()
@@ -218,6 +233,7 @@ def main():
     env_case(ref_env, "exprisk", 24, N=5, R=16, B=3, sigma_scale=0.1, err_mrad=400.0, helio_fn=readme, exponential_risk=True)
     host_case(ref_env)
     com_case()
+    angular_case(ref_field)
 
     # ---- shapes that route to the tcgen05 kernels (R >= 48): the tensor-core path pinned on the reference itself ----
     # BASELINE.json configs[0]/[1]: README quick start, N=50, 128x128, B=25, sigma_scale 0.1, 90 mrad

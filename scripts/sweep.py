@@ -49,9 +49,9 @@ def main():
         helio, targ_pos, targ_norm, area, _ = bench.make_inputs(N, B, rank=rank)
         torch.manual_seed(42 + rank)
         kw = dict(heliostat_pos=helio.to(dev), targ_pos=targ_pos.to(dev), targ_area=area, targ_norm=targ_norm.to(dev), sigma_scale=0.01,
-                  error_scale_mrad=90.0, resolution=R, device=str(dev), new_errors_every_reset=True, check_finite=False)
-        torch.cuda.synchronize(); t0 = time.perf_counter()
-        env = make_sharded_env(HelioEnv, global_batch_size=B * world, **kw) if world > 1 else HelioEnv(batch_size=B, **kw)
+                  error_scale_mrad=90.0, resolution=R, device=str(dev), new_errors_every_reset=True)   # product defaults: target cached,
+        torch.cuda.synchronize(); t0 = time.perf_counter()                                             # finite check on, graph="auto"
+        env = make_sharded_env(HelioEnv, global_batch_size=B * world, seed=42, **kw) if world > 1 else HelioEnv(batch_size=B, **kw)
         impl = dict(auto=0, simt=1, tc=2)[args.splat]
         env.noisy_field.splat_impl = env.ref_field.splat_impl = impl
         env.reset()
@@ -70,7 +70,6 @@ def main():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        Fn.reset_profile(True)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
@@ -81,17 +80,20 @@ def main():
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         ms = float(ms)
+        replayed = getattr(env, "_step_graph", None) is not None
+        Fn.reset_profile(True)                                   # per-kernel times: eager steps (event pairs cannot go into a graph)
+        for _ in range(3):
+            step()
         prof = Fn.collect_profile()
         Fn.reset_profile(False)
         evals = float(B) * world * N * R * R
         k = {n: round(v["avg_ms"] * 1e3, 1) for n, v in sorted(prof.items())}
-        t_tensor = 3 * 2.0 * B * N * R * R / (tensor_peak * 1e12) * 1e3            # 2 fwd renders + bwd = 8 FLOP/eval... (2+2+4)
-        t_tensor = 8.0 * B * N * R * R / (tensor_peak * 1e12) * 1e3
-        t_hbm = (36.0 * B * R * R + 140.0 * B * N) / (hbm_peak * 1e9) * 1e3          # images: 2 writes + 7 reads/writes of 4 B; per-(b,n) streams
+        t_tensor = 6.0 * B * N * R * R / (tensor_peak * 1e12) * 1e3                  # noisy render fwd (2) + bwd (4) FLOP/eval; target cached
+        t_hbm = (32.0 * B * R * R + 120.0 * B * N) / (hbm_peak * 1e9) * 1e3          # images: 1 write + 7 reads/writes of 4 B; per-(b,n) streams
         line = dict(N=N, R=R, B_per_gpu=B, n_gpus=world, splat=args.splat, ms_per_step=round(ms, 4), env_steps_per_s=round(1e3 / ms, 2),
                     evals_per_s=evals / (ms * 1e-3), roofline_ms=dict(tensor=round(t_tensor, 4), hbm=round(t_hbm, 4)),
                     frac_of_roofline=round(max(t_tensor, t_hbm) / ms, 4), bound="tensor" if t_tensor > t_hbm else "hbm",
-                    kernels_us=k, setup_s=round(setup_s, 3), mem_gb=round(torch.cuda.max_memory_allocated() / 1e9, 2))
+                    graph_replay=replayed, kernels_us=k, setup_s=round(setup_s, 3), mem_gb=round(torch.cuda.max_memory_allocated() / 1e9, 2))
         if args.cpu and rank == 0:
             if (N, R) not in cpu_cache:
                 f = bench.cpu_step_factory(N, R, 1, os.cpu_count() or 1)
