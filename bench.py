@@ -452,6 +452,10 @@ def main_ours(args):
     ms_total = timed(lambda: one_step(action0), steps)
     launches = Fn.launch_count() - launches0
     clocks = sampler.stop() if sampler else None
+    try:
+        mhz_fwd, mhz_bwd = Fn.tc_clock_mhz()          # SM clock the tcgen05 kernels HELD (measured inside the kernels)
+    except Exception:
+        mhz_fwd = mhz_bwd = 0.0
     kprof = Fn.collect_profile()
     Fn.reset_profile(False)
     ms_step = ms_total / steps
@@ -567,13 +571,21 @@ def main_ours(args):
         pass
     sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
     n_sms = torch.cuda.get_device_properties(dev).multi_processor_count
-    k_pad = (N + 31) // 32 * 32 if dom == "splat_fwd" else N        # the forward pads K = heliostats to 32 per stage
-    executed = 3.0 * flops_launch * (k_pad / float(N))              # 3 tcgen05.mma per algorithmic MAC (hi*hi, hi*lo, lo*hi)
+    # executed tensor work: 3 tcgen05.mma per algorithmic MAC (hi*hi, hi*lo, lo*hi); the forward pads K = heliostats to 32 per
+    # stage, the backward pads the heliostat rows of a tile to 128 per CTA (256 per CTA pair at R > 128)
+    pad = ((N + 31) // 32 * 32) / float(N) if dom == "splat_fwd" else ((N + 255) // 256 * 256 if R > 128 else (N + 127) // 128 * 128) / float(N)
+    executed = 3.0 * flops_launch * pad
     pipe_frac = executed / (avg_ms * 1e-3) / (n_sms * 4096.0 * sm_mhz * 1e6)
+    mhz_dom = mhz_fwd if dom == "splat_fwd" else mhz_bwd
+    pipe_frac_held = executed / (avg_ms * 1e-3) / (n_sms * 4096.0 * mhz_dom * 1e6) if mhz_dom else None
     roofline = dict(bound="tensor", kernel=dom, achieved=achieved, peak=peak, unit="TFLOP/s", frac=achieved / peak, traffic=traffic,
                     peak_source=f"{peak_src}: bf16 {bf16:.0f} TFLOP/s sustained / 2 (TF32) / 3 (3xTF32)",
                     frac_of_burst_peak=achieved / (bf16_burst / 6.0), burst_peak=bf16_burst / 6.0,
                     tensor_pipe_frac=pipe_frac,
+                    sm_mhz_held_in_kernel=dict(splat_fwd=mhz_fwd, splat_bwd=mhz_bwd,
+                                               note="cycles / nanoseconds measured INSIDE the tcgen05 kernels (helio_tc_clock_mhz): B200 power-throttles under "
+                                                    "sustained tensor load while NVML keeps reporting the application clock"),
+                    tensor_pipe_frac_at_held_clock=pipe_frac_held,
                     tensor_pipe_note=f"executed tcgen05 FLOP (3 x algorithmic x K padding) / ({n_sms} SMs x 4096 TF32 FLOP/clk x {sm_mhz:.0f} MHz median under load)",
                     cublas_tf32_inrun_tflops=tf32, frac_of_cublas_tf32_over_3=achieved / (tf32 / 3.0),
                     frac_of_nominal_tf32_over_3=achieved / (1125.0 / 3.0),   # 2.25 PFLOP/s bf16 nominal / 2 / 3
@@ -640,7 +652,7 @@ def main_ours(args):
         except Exception as e:
             f16x3 = dict(error=repr(e))
         finally:
-            _lib.load().helio_set_fwd_precision(0)
+            _lib.load().helio_set_fwd_precision(2)     # default: auto (f16x3 up to R = 128, 3xTF32 above)
     small = None
     if world == 1 and not args.no_small_field:
         try:

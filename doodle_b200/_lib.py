@@ -25,7 +25,7 @@ EXPORTS = (
     "helio_com_fwd", "helio_com_bwd",
     "helio_cull_workspace_bytes", "helio_cull", "helio_splat_fwd_culled", "helio_splat_bwd_culled",
     "helio_loss_bwd_packed", "helio_loss_pack", "helio_step_partials_floats", "helio_step_fwd", "helio_step_bwd",
-    "helio_splat_fwd_feed", "helio_step_fwd_feed",
+    "helio_splat_fwd_feed", "helio_step_fwd_feed", "helio_tc_clock_mhz",
 )
 
 
@@ -124,6 +124,8 @@ def _declare(lib):
     lib.helio_step_fwd_feed.argtypes = [sp, p, p, p, p, p, i, i, i, i, i] + [p] * 16 + [p, i64, C.POINTER(Feed), p]
     lib.helio_splat_fwd_feed.restype = i
     lib.helio_splat_fwd_feed.argtypes = [p, i, i, i, f, f, p, i, C.POINTER(Feed), p]
+    lib.helio_tc_clock_mhz.restype = i
+    lib.helio_tc_clock_mhz.argtypes = [i, C.POINTER(C.c_float)]
     lib.helio_step_partials_floats.restype = i64
     lib.helio_step_partials_floats.argtypes = [i, i, i, i]
     lib.helio_step_bwd.restype = i

@@ -64,13 +64,23 @@ std::atomic<int>& tc_pair_state() {
 }
 int tc_pair_mode() { return tc_pair_state().load(std::memory_order_relaxed); }
 
-// forward splat operand precision: 0 = 3xTF32 (default), 1 = two fp16 pieces of the 2^14-scaled Gaussians (opt-in)
+// forward splat operand format: 0 = 3xTF32 everywhere, 1 = f16x3 everywhere (two fp16 pieces of the 2^14-scaled Gaussians),
+// 2 = auto (default): f16x3 for images up to 128 pixels a side, 3xTF32 above.  Both carry 22 significant bits per operand;
+// measured error against fp64 of f16x3 is not larger than 3xTF32's at any tested shape (test_forward_f16x3_...).  At
+// R <= 128 a CTA generates as many operand rows per stage as at R = 256 for half (a quarter) of the MMAs, so the kernel is
+// bound by operand generation and the cheaper MMAs / half-size stages of f16x3 pay (-3 ... -12 % measured); at R = 256 the
+// headline configuration keeps the 3xTF32 contraction BASELINE.json names.
 std::atomic<int>& fwd_prec_state() {
     static std::atomic<int> mode{[]() {
         const char* e = std::getenv("HELIO_FWD_PREC");
-        return (e && std::atoi(e) == 1) ? 1 : 0;
+        const int v = e ? std::atoi(e) : 2;
+        return (v >= 0 && v <= 2) ? v : 2;
     }()};
     return mode;
+}
+int fwd_prec_for(int R) {
+    const int m = fwd_prec_state().load(std::memory_order_relaxed);
+    return m == 2 ? (R <= 128 ? 1 : 0) : m;
 }
 
 // ---- opt-in per-kernel timing (helio_profile_*): CUDA events recorded around every kernel this library
@@ -154,8 +164,31 @@ HELIO_API int helio_profile_get(int index, const char** name, float* ms) {
     return 0;
 }
 
+#if HELIO_TC_STATS
+// debug builds only (-DHELIO_TC_STATS=1, scripts/tc_stats.py): copy out / clear the per-warp cycle counters of the last
+// tcgen05 kernel.  out: [160][16][4] uint64.
+HELIO_API int helio_debug_tc_stats(unsigned long long* out_host, int clear) {
+    HELIO_CUDA_OK(cudaDeviceSynchronize());
+    if (out_host) HELIO_CUDA_OK(cudaMemcpyFromSymbol(out_host, g_tc_stats, sizeof(g_tc_stats)));
+    if (clear) {
+        void* p = nullptr;
+        HELIO_CUDA_OK(cudaGetSymbolAddress(&p, g_tc_stats));
+        HELIO_CUDA_OK(cudaMemset(p, 0, sizeof(g_tc_stats)));
+    }
+    return 0;
+}
+#endif
+
+HELIO_API int helio_tc_clock_mhz(int which, float* mhz_host) {
+    HELIO_REQUIRE((which == 0 || which == 1) && mhz_host, "which must be 0 (forward) or 1 (backward)");
+    unsigned long long v[2][2];
+    HELIO_CUDA_OK(cudaMemcpyFromSymbol(v, g_tc_clock, sizeof(v)));     // synchronises with the device
+    *mhz_host = v[which][1] ? (float)((double)v[which][0] * 1e3 / (double)v[which][1]) : 0.f;
+    return 0;
+}
+
 HELIO_API int helio_set_fwd_precision(int mode) {
-    if (mode != 0 && mode != 1) return set_error(HELIO_E_BADARG, "bad argument: %s%s", "forward precision mode must be 0 or 1");
+    if (mode < 0 || mode > 2) return set_error(HELIO_E_BADARG, "bad argument: %s%s", "forward precision mode must be 0, 1 or 2");
     fwd_prec_state().store(mode, std::memory_order_relaxed);
     return 0;
 }
@@ -222,7 +255,7 @@ int splat_fwd_impl(const float* params, int B, int N, int R, float width, float 
             return e ? std::atoi(e) : 0;
         }();
         HELIO_CUDA_OK(splat_tc_fwd(params, img, B, N, R, width, height, d->sms, (cudaStream_t)stream, tc_pair_mode(), split, fuse, fz, counts,
-                                   fwd_prec_state().load(std::memory_order_relaxed)));
+                                   fwd_prec_for(R)));
     } else {
         HELIO_REQUIRE(fuse == kFuseNone && counts == nullptr, "epilogue fusion / culled input need the tcgen05 path");
         HELIO_CUDA_OK(splat_fwd_simt(params, img, B, N, R, width, height, d->sms, (cudaStream_t)stream));

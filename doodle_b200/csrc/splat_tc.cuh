@@ -42,9 +42,67 @@
 #define HELIO_BWD_DEFER 0
 #endif
 
+#ifndef HELIO_FWD_PREFETCH2
+// 1: forward producers keep the footprint parameters two stages ahead in two register buffers, the loads issued after the
+// proxy fence.  Measured on B200 (scripts/gpu_ab_fwd.sh): the fence wait drops from 14 % to 8 % of a producer warp's time,
+// but the second buffer needs 16 more registers, the kernel hits the 128-register ceiling of a 13-warp CTA (four warps
+// share one scheduler's 16 K registers), ptxas spills, and the forward gets SLOWER (3.51 -> 4.5 ms).  Kept as an A/B switch.
+#define HELIO_FWD_PREFETCH2 0
+#endif
+#ifndef HELIO_RELAXED_ARRIVE
+#define HELIO_RELAXED_ARRIVE 0   // 1: producers signal "stage written" with mbarrier.arrive.relaxed (see tc_common.cuh)
+#endif
+#ifndef HELIO_TC_STATS
+#define HELIO_TC_STATS 0    // 1: per-warp cycle accounting of the pipeline roles (debug builds only; scripts/tc_stats.py)
+#endif
+
 namespace helio {
 
+#if HELIO_TC_STATS
+// [CTA][warp][slot]: 0 = total cycles in the role loop, 1..3 = cycles blocked in the role's waits (see the kernels)
+__device__ unsigned long long g_tc_stats[160][16][4];
+__device__ __forceinline__ unsigned long long tc_clock() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(t));
+    return t;
+}
+struct TcStat {
+    unsigned long long t0, acc[4];
+    __device__ TcStat() : t0(tc_clock()), acc{0, 0, 0, 0} {}
+    __device__ void flush() {
+        acc[0] = tc_clock() - t0;
+        if ((threadIdx.x & 31) == 0 && blockIdx.x < 160)
+            for (int k = 0; k < 4; ++k) g_tc_stats[blockIdx.x][threadIdx.x >> 5][k] = acc[k];
+    }
+};
+#define TC_STAT_DECL TcStat tcst
+#define TC_STAT_BEGIN unsigned long long tcs_t = tc_clock()
+#define TC_STAT_END(slot) tcst.acc[slot] += tc_clock() - tcs_t
+#define TC_STAT_FLUSH tcst.flush()
+#else
+#define TC_STAT_DECL
+#define TC_STAT_BEGIN
+#define TC_STAT_END(slot)
+#define TC_STAT_FLUSH
+#endif
+
 constexpr int kTcMaxR = 1024;  // coordinate tables live in shared memory
+
+// Always-on clock probe: CTA 0 of a tcgen05 kernel leaves {SM cycles, nanoseconds} of its own lifetime here ([0] forward,
+// [1] backward), i.e. the SM clock the kernel actually HELD (B200 power-throttles inside these kernels: ~1.6-1.8 GHz
+// under full tensor load while NVML still reports the 1965 MHz application clock).  helio_tc_clock_mhz reads it; bench.py
+// quotes the tensor-pipe utilisation at this clock.
+__device__ unsigned long long g_tc_clock[2][2];
+__device__ __forceinline__ unsigned long long probe_cycles() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ unsigned long long probe_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
 // ------------------------------------------------------------------------------------------------
 // pieces shared by both kernels
@@ -82,7 +140,7 @@ struct SplatTcLayout {
     static_assert(BROWS * CG == NT, "each CTA of the group stages NT / CG rows of B");
     static_assert(kTmemCols <= 512 && (kTmemCols & (kTmemCols - 1)) == 0 && kTmemCols >= 32, "TMEM columns");
     static_assert(kStages >= 2 && kSmemBytes <= 227 * 1024, "shared memory budget");
-    static_assert((2 * kStages + 4) * 8 + 8 <= 256, "barrier block");
+    static_assert((2 * kStages + 4) * 8 + 8 <= 224, "barrier block (the last 32 bytes hold the clock probe)");
 };
 
 // shared-memory carve-up + one-time setup common to the forward and backward kernels
@@ -96,6 +154,7 @@ struct SplatTcCtx {
     uint32_t epi_u;       // epilogue staging buffer (32-bit shared address)
     uint32_t tmem_base;
     uint32_t rank;        // CTA rank inside the pair (0 when CG == 1)
+    uint64_t* probe;      // clock probe start values (CTA 0, thread 0)
 
     __device__ __forceinline__ void setup(uint8_t* smem_raw, int R, const Axis& ax, const Axis& ay) {
         smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -109,6 +168,8 @@ struct SplatTcCtx {
         tempty = tfull + 2;                // [2]        epilogue -> MMA   (leader's copy is the live one)
         uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
         epi_u = tc::smem_u32(reinterpret_cast<uint8_t*>(bars) + 256);
+        probe = bars + 28;                 // bytes 224..239 of the barrier block
+        if (blockIdx.x == 0 && threadIdx.x == 0) probe[0] = probe_cycles(), probe[1] = probe_ns();
         rank = CG == 2 ? tc::cluster_ctarank() : 0u;
         const int warp = threadIdx.x >> 5;
 
@@ -144,9 +205,13 @@ struct SplatTcCtx {
         tmem_base = *tmem_slot;
     }
 
-    __device__ __forceinline__ void teardown() {
+    __device__ __forceinline__ void teardown(int which) {
         tc::tc_fence_before();
         __syncthreads();
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            g_tc_clock[which][0] = probe_cycles() - probe[0];
+            g_tc_clock[which][1] = probe_ns() - probe[1];
+        }
         if constexpr (CG == 2) tc::cluster_sync();   // no CTA leaves while its peer may still signal it
         if ((threadIdx.x >> 5) == C::kMmaWarp) {
             tc::tc_fence_after();
@@ -160,8 +225,13 @@ struct SplatTcCtx {
         tc::fence_proxy_async_smem();
         __syncwarp();
         if ((threadIdx.x & 31) == 0) {
+#if HELIO_RELAXED_ARRIVE
+            if constexpr (CG == 2) tc::mbar_arrive_remote_relaxed(&full[s], 0);
+            else tc::mbar_arrive_relaxed(&full[s]);
+#else
             if constexpr (CG == 2) tc::mbar_arrive_remote(&full[s], 0);
             else tc::mbar_arrive(&full[s]);
+#endif
         }
     }
     // producer warp: wait until the MMAs that read stage s have retired
@@ -328,9 +398,9 @@ splat_fwd_tc_kernel(const float4* __restrict__ params, const int* __restrict__ c
             return (row >> 3) * 1024u + (row & 7u) * 128u + ((((uint32_t)ch) ^ (row & 7u)) << 4);
         };
         uint32_t it = 0;                             // global stage counter
-#if HELIO_FWD_DEFER
+        TC_STAT_DECL;
         int pending = -1;                            // stage whose stores are issued but not yet handed to the MMA warp
-#endif
+        static_assert(HELIO_FWD_DEFER == 1, "the forward producers are written for the deferred hand-off (measured: -5.7 %)");
         for (int tile = group; tile < num_tiles; tile += ngroups) {
             const int b = tile / tiles_per_img, t = tile % tiles_per_img;
             const int g0 = (isA ? (t / tiles_j) * kTileM + (int)cx.rank * C::kM : (t % tiles_j) * NT + (int)cx.rank * C::kBRows) + wrow;
@@ -343,15 +413,18 @@ splat_fwd_tc_kernel(const float4* __restrict__ params, const int* __restrict__ c
             for (int st = 0; st < kSteps; ++st) xr[st] = tc::lds_f32(tab + 4u * kRS * st);
             const float4* pb = params + (size_t)b * N;
             const int cnt = sun_count(b), nchunks = sun_chunks(cnt), last = max(cnt, 1) - 1;
-            // this lane's 4 heliostats of the stage, prefetched one stage ahead as raw float4 (index clamped so the
-            // load never needs a select: nothing touches the loaded registers until the next stage decodes them)
-            float4 pr[4];
-            auto prefetch = [&](int c) {
+            // This lane's 4 heliostats of a stage arrive as raw float4 (index clamped so the load never needs a select),
+            // prefetched one stage ahead into the buffer the current stage has just decoded.  The hand-over's
+            // fence.proxy.async compiles to MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC, and the MEMBAR waits for every outstanding
+            // memory operation of the thread, i.e. for what is left of the L2 latency of that prefetch: 14 % of a producer
+            // warp's time (scripts/tc_stats.py).  HELIO_FWD_PREFETCH2 = 1 moves the loads behind the fence, two stages ahead in
+            // two buffers (even / odd stages) -- see the note at its definition for why that is not the default.
+            float4 prA[4], prB[4];
+            auto load_params = [&](float4 (&pr)[4], int c) {
 #pragma unroll
                 for (int e = 0; e < 4; ++e) pr[e] = __ldg(pb + min(c * C::kKC + 4 * ch + e, last));
             };
-            prefetch(0);
-            for (int c = 0; c < nchunks; ++c, ++it) {
+            auto stage = [&](float4 (&pr)[4], const int c) {
                 float ctr[4], nk2[4], la[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
@@ -362,11 +435,12 @@ splat_fwd_tc_kernel(const float4* __restrict__ params, const int* __restrict__ c
                     // K padding: 2^-inf = exact zeros
                     la[e] = have ? (isA ? __log2f(pr[e].w) : 0.f) + (PREC == 1 ? 14.f : 0.f) : -INFINITY;   // f16x3: operands x 2^14
                 }
-                prefetch(c + 1 < nchunks ? c + 1 : c);
+#if !HELIO_FWD_PREFETCH2
+                load_params(pr, c + 1 < nchunks ? c + 1 : c);      // A/B: the old one-stage-ahead prefetch (same buffer)
+#endif
                 const int s = it % C::kStages;
-#if HELIO_FWD_DEFER
-                // Hand the PREVIOUS stage over only now: its shared-memory stores drain while this stage's Gaussians
-                // are evaluated, so the fence in producer_commit finds nothing left to wait for.
+                // Hand the PREVIOUS stage over only after this stage's Gaussians have been evaluated: its shared-memory
+                // stores drain under the arithmetic.
                 float v[kSteps][4];
                 if (!dead) {
 #if HELIO_PACKED2
@@ -401,8 +475,19 @@ splat_fwd_tc_kernel(const float4* __restrict__ params, const int* __restrict__ c
                         }
 #endif
                 }
-                if (pending >= 0) cx.producer_commit(pending);
-                cx.producer_acquire(s, (it / C::kStages) & 1);
+                {
+                    TC_STAT_BEGIN;
+                    if (pending >= 0) cx.producer_commit(pending);
+                    TC_STAT_END(1);
+                }
+#if HELIO_FWD_PREFETCH2
+                if (c + 2 < nchunks) load_params(pr, c + 2);       // this buffer's next stage; lands under two stages of work
+#endif
+                {
+                    TC_STAT_BEGIN;
+                    cx.producer_acquire(s, (it / C::kStages) & 1);
+                    TC_STAT_END(2);
+                }
                 const uint32_t base = cx.smem_u + (uint32_t)(s * C::kStageBytes) + region;
                 if constexpr (PREC == 1) {
                     // two fp16 pieces per value, packed [p1 (8 bytes) ... | p2 ...]: this lane's 4 heliostats are bytes
@@ -444,59 +529,69 @@ splat_fwd_tc_kernel(const float4* __restrict__ params, const int* __restrict__ c
                     }
                 }
                 pending = s;
-#else
-                static_assert(PREC == 0, "the f16x3 producers are written for the deferred hand-off");
-                cx.producer_acquire(s, (it / C::kStages) & 1);
-                const uint32_t base = cx.smem_u + (uint32_t)(s * C::kStageBytes) + region;
-                if (!dead)
-#pragma unroll
-                for (int st = 0; st < kSteps; ++st) {
-                    float hi[4], lo[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const float d = xr[st] - ctr[e];
-                        const float v = ex2(fmaf(d * nk2[e], d, la[e]));
-                        tc::split_tf32(v, hi[e], lo[e]);
-                    }
-                    const uint32_t dst = base + row_off(st);
-                    tc::sts_v4(dst, hi[0], hi[1], hi[2], hi[3]);
-                    tc::sts_v4(dst + lo_delta, lo[0], lo[1], lo[2], lo[3]);
-                }
-                cx.producer_commit(s);
-#endif
+                ++it;
+            };
+#if HELIO_FWD_PREFETCH2
+            load_params(prA, 0);
+            if (nchunks > 1) load_params(prB, 1);
+#pragma unroll 1
+            for (int c = 0; c < nchunks; c += 2) {
+                stage(prA, c);
+                if (c + 1 < nchunks) stage(prB, c + 1);
             }
+#else
+            load_params(prA, 0);
+#pragma unroll 1
+            for (int c = 0; c < nchunks; ++c) stage(prA, c);
+#endif
         }
 #if HELIO_FWD_DEFER
         if (pending >= 0) cx.producer_commit(pending);
 #endif
+        TC_STAT_FLUSH;
     } else if (warp == C::kMmaWarp) {
         // ================= MMA issuer (leader CTA of the group) =================
         if (cx.rank == 0) {
+            TC_STAT_DECL;
             uint32_t it = 0, tcount = 0;
             for (int tile = group; tile < num_tiles; tile += ngroups, ++tcount) {
                 const int acc = tcount & 1;
                 const int nchunks = sun_chunks(sun_count(tile / tiles_per_img));
-                cx.mma_wait_tempty(acc, (tcount >> 1) & 1);
+                {
+                    TC_STAT_BEGIN;
+                    cx.mma_wait_tempty(acc, (tcount >> 1) & 1);
+                    TC_STAT_END(1);
+                }
                 const uint32_t d_tmem = cx.tmem_base + (uint32_t)(acc * NT);
                 for (int c = 0; c < nchunks; ++c, ++it) {
                     const int s = it % C::kStages;
-                    cx.mma_wait_full(s, (it / C::kStages) & 1);
+                    {
+                        TC_STAT_BEGIN;
+                        cx.mma_wait_full(s, (it / C::kStages) & 1);
+                        TC_STAT_END(2);
+                    }
                     if (tc::elect_one()) cx.issue_stage(s, d_tmem, c == 0, c == nchunks - 1, acc);
                     __syncwarp();
                 }
             }
+            TC_STAT_FLUSH;
         }
     } else {
         // ================= epilogue =================
         const int q = warp & 3;                      // TMEM lane quarter this warp may access
         uint32_t tcount = 0;
+        TC_STAT_DECL;
         for (int tile = group; tile < num_tiles; tile += ngroups, ++tcount) {
             const int b = tile / tiles_per_img, t = tile % tiles_per_img;
             const int i0 = (t / tiles_j) * kTileM + (int)cx.rank * C::kM, j0 = (t % tiles_j) * NT;
             const int acc = tcount & 1;
             float tinv_t = 1.f;                      // kFuseLoss: the image's normaliser, fetched before the wait
             if constexpr (FUSE == kFuseLoss) tinv_t = fmaxf(__ldg(fz.tx + b), 1e-6f);
-            tc::mbar_wait_sleep(&cx.tfull[acc], (tcount >> 1) & 1);
+            {
+                TC_STAT_BEGIN;
+                tc::mbar_wait_sleep(&cx.tfull[acc], (tcount >> 1) & 1);
+                TC_STAT_END(1);
+            }
             tc::tc_fence_after();
             const int i = i0 + q * 32 + lane;
             const size_t row_off = ((size_t)b * R + i) * R + j0;
@@ -620,8 +715,9 @@ splat_fwd_tc_kernel(const float4* __restrict__ params, const int* __restrict__ c
                 }
             }
         }
+        TC_STAT_FLUSH;
     }
-    cx.teardown();
+    cx.teardown(0);
 }
 
 inline bool splat_tc_fwd_supported(int B, int N, int R) { return B > 0 && N > 0 && R >= 8 && R <= kTcMaxR; }
@@ -774,6 +870,7 @@ splat_bwd_tc_kernel(const float4* __restrict__ params, const int* __restrict__ c
         };
         bool live_next;
         float4 p_next = tile_params(group, live_next);
+        TC_STAT_DECL;
 #if HELIO_BWD_DEFER
         int pending = -1;
 #endif
@@ -823,7 +920,11 @@ splat_bwd_tc_kernel(const float4* __restrict__ params, const int* __restrict__ c
                         }
                         pending = s;
 #else
-                        cx.producer_acquire(s, (it / C::kStages) & 1);
+                        {
+                            TC_STAT_BEGIN;
+                            cx.producer_acquire(s, (it / C::kStages) & 1);
+                            TC_STAT_END(2);
+                        }
                         const uint32_t hi_base = cx.smem_u + (uint32_t)(s * C::kStageBytes);
                         const uint32_t lo_base = hi_base + C::kABytes;
 #pragma unroll
@@ -841,7 +942,11 @@ splat_bwd_tc_kernel(const float4* __restrict__ params, const int* __restrict__ c
                             tc::sts_v4(hi_base + off, hi[0], hi[1], hi[2], hi[3]);
                             tc::sts_v4(lo_base + off, lo[0], lo[1], lo[2], lo[3]);
                         }
-                        cx.producer_commit(s);
+                        {
+                            TC_STAT_BEGIN;
+                            cx.producer_commit(s);
+                            TC_STAT_END(1);
+                        }
 #endif
                     }
                 }
@@ -850,12 +955,14 @@ splat_bwd_tc_kernel(const float4* __restrict__ params, const int* __restrict__ c
 #if HELIO_BWD_DEFER
         if (pending >= 0) cx.producer_commit(pending);
 #endif
+        TC_STAT_FLUSH;
     } else if (warp < C::kMmaWarp) {
         // ================= gradient tile stagers =================
         const int t = threadIdx.x - C::kAWarps * 32;     // 0..kBRows-1: operand row inside this CTA's share
         const int gw = t >> 5;
         const int row_base = (int)cx.rank * C::kBRows;   // first accumulator column this CTA stages
         uint32_t it = 0;
+        TC_STAT_DECL;
 #if HELIO_BWD_DEFER
         int spending = -1;
 #endif
@@ -935,7 +1042,11 @@ splat_bwd_tc_kernel(const float4* __restrict__ params, const int* __restrict__ c
 #if HELIO_BWD_DEFER
                         if (spending >= 0) cx.producer_commit(spending);   // previous stage: drained under the loads above
 #endif
-                        cx.producer_acquire(s, (it / C::kStages) & 1);
+                        {
+                            TC_STAT_BEGIN;
+                            cx.producer_acquire(s, (it / C::kStages) & 1);
+                            TC_STAT_END(2);
+                        }
                         const uint32_t hi_base = cx.smem_u + (uint32_t)(s * C::kStageBytes + 2 * C::kABytes);
                         const uint32_t lo_base = hi_base + C::kBBytes;
 #pragma unroll
@@ -951,7 +1062,11 @@ splat_bwd_tc_kernel(const float4* __restrict__ params, const int* __restrict__ c
 #if HELIO_BWD_DEFER
                         spending = s;
 #else
-                        cx.producer_commit(s);
+                        {
+                            TC_STAT_BEGIN;
+                            cx.producer_commit(s);
+                            TC_STAT_END(1);
+                        }
 #endif
                     }
                 }
@@ -960,25 +1075,36 @@ splat_bwd_tc_kernel(const float4* __restrict__ params, const int* __restrict__ c
 #if HELIO_BWD_DEFER
         if (spending >= 0) cx.producer_commit(spending);
 #endif
+        TC_STAT_FLUSH;
     } else if (warp == C::kMmaWarp) {
         // ================= MMA issuer (leader CTA of the group) =================
         if (cx.rank == 0) {
+            TC_STAT_DECL;
             uint32_t it = 0, sub = 0;
             const int subs_per_tile = 2 * pblocks;
             for (int tile = group; tile < num_tiles; tile += ngroups) {
                 if (tile_empty(tile)) continue;
                 for (int sb = 0; sb < subs_per_tile; ++sb, ++sub) {
                     const int acc = sub & 1;
-                    cx.mma_wait_tempty(acc, (sub >> 1) & 1);
+                    {
+                        TC_STAT_BEGIN;
+                        cx.mma_wait_tempty(acc, (sub >> 1) & 1);
+                        TC_STAT_END(1);
+                    }
                     const uint32_t d_tmem = cx.tmem_base + (uint32_t)(acc * NT);
                     for (int c = 0; c < kchunks; ++c, ++it) {
                         const int s = it % C::kStages;
-                        cx.mma_wait_full(s, (it / C::kStages) & 1);
+                        {
+                            TC_STAT_BEGIN;
+                            cx.mma_wait_full(s, (it / C::kStages) & 1);
+                            TC_STAT_END(2);
+                        }
                         if (tc::elect_one()) cx.issue_stage(s, d_tmem, c == 0, c == kchunks - 1, acc);
                         __syncwarp();
                     }
                 }
             }
+            TC_STAT_FLUSH;
         }
     } else {
         // ================= epilogue: accumulator -> moments =================
@@ -992,6 +1118,7 @@ splat_bwd_tc_kernel(const float4* __restrict__ params, const int* __restrict__ c
         };
         bool live_next;
         float4 p_next = tile_params(group, live_next);
+        TC_STAT_DECL;
         for (int tile = group; tile < num_tiles; tile += ngroups) {
             const int b = tile / nblocks, nb = tile % nblocks;
             const int n = nb * kTileH + (int)cx.rank * C::kM + q * 32 + lane;
@@ -1009,7 +1136,11 @@ splat_bwd_tc_kernel(const float4* __restrict__ params, const int* __restrict__ c
 #pragma unroll 1
                 for (int pbk = 0; pbk < pblocks; ++pbk, ++sub) {
                     const int acc = sub & 1;
-                    tc::mbar_wait_sleep(&cx.tfull[acc], (sub >> 1) & 1);
+                    {
+                        TC_STAT_BEGIN;
+                        tc::mbar_wait_sleep(&cx.tfull[acc], (sub >> 1) & 1);
+                        TC_STAT_END(1);
+                    }
                     tc::tc_fence_after();
                     const uint32_t taddr = cx.tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * NT);
                     const int col0 = pbk * NT;
@@ -1044,8 +1175,9 @@ splat_bwd_tc_kernel(const float4* __restrict__ params, const int* __restrict__ c
             }
             if (live) moments[(size_t)b * N + (index ? __ldg(index + (size_t)b * N + n) : n)] = make_float4(S0, Sx, Sy, S2);
         }
+        TC_STAT_FLUSH;
     }
-    cx.teardown();
+    cx.teardown(1);
 }
 
 inline bool splat_tc_bwd_supported(int B, int N, int R) { return B > 0 && N > 0 && R >= 8 && R <= kTcMaxR; }

@@ -65,6 +65,17 @@ def collect_profile():
     return out
 
 
+def tc_clock_mhz():
+    """(forward, backward) SM clock in MHz held inside the most recent tcgen05 splat kernels (helio_tc_clock_mhz; syncs)."""
+    lib = _lib.load()
+    out = []
+    for which in (0, 1):
+        v = C.c_float()
+        _lib.check(lib.helio_tc_clock_mhz(which, C.byref(v)), "helio_tc_clock_mhz")
+        out.append(float(v.value))
+    return tuple(out)
+
+
 class _Call:
     """Context manager around one C-ABI launch: device guard (only when the tensors live on another
     device than the current one) and launch count."""

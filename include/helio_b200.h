@@ -71,11 +71,12 @@ HELIO_API int helio_device_ok(void);
  * No reference counterpart (tuning / A-B switch of this library). */
 HELIO_API int helio_set_tc_pair_mode(int mode);
 
-/* Forward splat operand format on the tcgen05 path.  0 (default): 3xTF32.  1 (opt-in, experimental): both
- * operands of the forward are Gaussians in [0,1]; they are scaled by 2^14 and split into two fp16 pieces
- * (11 + 11 significant bits, the accuracy the tf32 hi/lo split keeps), three kind::f16 MMAs per K-step,
- * fp32 accumulation, exact 2^-28 unscale in the epilogue.  Process-wide; initial value from HELIO_FWD_PREC.
- * The backward (unbounded image gradient) always uses 3xTF32. */
+/* Forward splat operand format on the tcgen05 path.  0: 3xTF32 everywhere.  1: "f16x3" everywhere -- both operands of
+ * the forward are Gaussians in [0,1]; they are scaled by 2^14 and split into two fp16 pieces (11 + 11 significant bits,
+ * the accuracy the tf32 hi/lo split keeps), three kind::f16 MMAs per K-step, fp32 accumulation, exact 2^-28 unscale in
+ * the epilogue.  2 (default): auto = f16x3 for images up to 128 pixels a side (operand-generation-bound shapes, where
+ * its half-size stages and cheaper MMAs pay), 3xTF32 above (the contraction BASELINE.json names for the headline shape).
+ * Process-wide; initial value from HELIO_FWD_PREC.  The backward (unbounded image gradient) always uses 3xTF32. */
 HELIO_API int helio_set_fwd_precision(int mode);
 
 /* Opt-in per-kernel timing (no reference counterpart; SURVEY.md section 5 "tracing / profiling").
@@ -87,6 +88,12 @@ HELIO_API int helio_set_fwd_precision(int mode);
 HELIO_API int helio_profile_enable(int on);
 HELIO_API int helio_profile_count(void);
 HELIO_API int helio_profile_get(int index, const char** name, float* ms);
+
+/* Diagnostic (no reference counterpart): SM clock in MHz that CTA 0 of the most recent tcgen05 splat kernel held over its
+ * lifetime (which = 0 forward, 1 backward; cycles / wall nanoseconds measured inside the kernel).  B200 power-throttles
+ * under sustained tensor load, so this -- not the application clock NVML reports -- is the clock the roofline of those
+ * kernels should be quoted at.  Synchronises with the device.  0 if that kernel has not run. */
+HELIO_API int helio_tc_clock_mhz(int which, float* mhz_host);
 
 /* Bytes of workspace helio_geom_fwd needs for (B, N) (block partials + ticket counter).  The
  * workspace must be zero-initialised ONCE by the caller; the kernel leaves it zeroed.  A workspace holds
