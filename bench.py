@@ -664,7 +664,7 @@ def main_ours(args):
                 ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
                 env_steps_per_s=1e3 / ms_step,
                 config=dict(workload=WORKLOAD["name"], N=N, R=R, B_per_gpu=B, global_batch=B * world, parallelism=f"dp{world}",
-                            splat=args.splat, target_cached=cached, check_finite=True,
+                            splat=args.splat, target_cached=cached, check_finite="on (product default: asserts of step t raised at the next entry, no device sync)",
                             l2="inputs larger than L2 (>= 3 GB of images per step)",
                             renders_per_step="noisy fwd+bwd (target image cached: exact, it depends on the suns only)" if cached
                             else "noisy fwd+bwd, target fwd (re-rendered every step as in the reference)"),

@@ -9,7 +9,11 @@ EDT distance maps) are restated here; the per-step work runs in K1-K4.
 Differences, all opt-in or bug-compatible:
   * ``new_sun_pos_every_reset=True`` works (the reference calls a method that does not exist,
     test_environment.py:379);
-  * the six NaN/Inf asserts (test_environment.py:495-501) read ONE fused device flag (one sync);
+  * the six NaN/Inf asserts (test_environment.py:495-501) read ONE fused triple {mse, dist, bound}.  ``check_finite=True``
+    (default) copies it to pinned host memory without synchronising and raises the asserts of step t at the NEXT entry
+    into the env (step / reset / set_sun_pos / ``flush_checks()``): a step never stalls the device, so the host can
+    queue the backward while the forward still runs.  ``check_finite="sync"`` restores the reference's immediate
+    asserts (one device sync per step); ``False`` switches them off;
   * ``fused_step`` (keyword-only, default True): ``step`` runs as one C-ABI call forward and one backward
     (helio_step_fwd / helio_step_bwd: the same kernels, far less host time for small fields); the
     error-mask and exponential-risk variants are formed from its per-image sums / per-heliostat bounds;
@@ -212,6 +216,11 @@ class HelioEnv(_EnvBase):
         self._copy_stream = None
         self.distance_maps_impl = distance_maps_impl   # "auto"/"cuda": GPU EDT; "scipy": the reference's host path
         self._target_cache = None
+        if check_finite not in (True, False, "sync"):
+            raise ValueError(f"check_finite must be True, False or 'sync' (got {check_finite!r})")
+        self._finite_host = None                       # pinned {mse, dist, bound} of the last eager step (deferred asserts)
+        self._finite_event = None
+        self._finite_pending = False
         if graph not in (True, False, "auto"):
             raise ValueError(f"graph must be True, False or 'auto' (got {graph!r})")
         # encoder feed: com=True adds monitor['com'] [B,2] = CenterOfMass2D(obs['img']) (differentiable),
@@ -352,13 +361,38 @@ class HelioEnv(_EnvBase):
 
     # ---- transparent CUDA-graph replay (graphs.StepGraph) ---------------------------------------------------------
     def _check_deferred(self):
-        """Graph mode raises the NaN/Inf asserts of step t here, at the next entry into the env (:495-501)."""
+        """The NaN/Inf asserts of step t (:495-501) are raised here, at the next entry into the env."""
         sg = getattr(self, "_step_graph", None)
         if sg is not None:
             sg.check_pending()
+        if getattr(self, "_finite_pending", False):
+            self._finite_pending = False
+            self._finite_event.synchronize()            # long done by the time the caller comes back
+            mse, dist_l, bound = self._finite_host.numpy().tolist()
+            if not (mse - mse == 0.0 and dist_l - dist_l == 0.0 and bound - bound == 0.0):
+                assert not math.isnan(mse), "MSE is NaN"
+                assert not math.isnan(dist_l), "Distance loss is NaN"
+                assert not math.isnan(bound), "Boundary loss is NaN"
+                assert not math.isinf(mse), "MSE is Inf"
+                assert not math.isinf(dist_l), "Distance loss is Inf"
+                assert not math.isinf(bound), "Boundary loss is Inf"
+
+    def flush_checks(self):
+        """Raise any pending NaN/Inf assert now (waits for the last step's forward)."""
+        self._check_deferred()
+
+    def _defer_finite(self, means: torch.Tensor):
+        if self._finite_host is None:
+            self._finite_host = torch.zeros(3, dtype=torch.float32, device="cpu").pin_memory()
+            self._finite_event = torch.cuda.Event()
+        self._finite_host.copy_(means.detach()[:3], non_blocking=True)
+        self._finite_event.record()
+        self._finite_pending = True
 
     def _graph_eligible(self, action) -> bool:
         if self.graph is False or not self.fused_step or self.cull or self.use_error_mask or self.exponential_risk or self.com:
+            return False
+        if self.check_finite == "sync":                 # immediate asserts need the eager step's device sync
             return False
         if not (isinstance(action, torch.Tensor) and action.is_cuda):
             return False
@@ -464,7 +498,9 @@ class HelioEnv(_EnvBase):
         means = self._reduce_means(packed)
         mse, dist_l, bound, alignment_loss = means.unbind(0)
 
-        if self.check_finite:                                                        # :495-501, one sync
+        if self.check_finite is True:                                                # :495-501, raised at the next entry: no sync
+            self._defer_finite(means)
+        elif self.check_finite == "sync":                                            # the reference's immediate asserts, one sync
             if not bool(torch.isfinite(means[:3]).all()):
                 assert not torch.isnan(mse).any(), "MSE is NaN"
                 assert not torch.isnan(dist_l).any(), "Distance loss is NaN"

@@ -350,7 +350,7 @@ class GraphedStep:
             if action is not None:
                 self.action.copy_(action.detach().reshape(self.action.shape))
         check, graph_mode = env.check_finite, env.graph
-        env.check_finite = False                       # a device->host sync cannot be captured
+        env.check_finite = False                       # the finite check is the caller's business here (read gstep.metrics)
         env.graph = False                              # the eager fused step is what gets captured here
         try:
             side = torch.cuda.Stream(device=self.action.device)
