@@ -374,6 +374,25 @@ def gpu_eager_numbers(torch, dev, N, R, budget_s=20.0):
                      "evals/s of a chunk is the rate of the full workload (independent suns)")
 
 
+def _leave_process_group(torch, dist, envs):
+    """Release captured graphs (a sharded small field's graphs hold NCCL kernels), then destroy the process group under a
+    watchdog: a hung teardown must not cost GPU time."""
+    import threading
+    for e in envs:
+        try:
+            if e is not None:
+                e.close()
+        except Exception:
+            pass
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    t = threading.Timer(30.0, lambda: os._exit(0))
+    t.daemon = True
+    t.start()
+    dist.destroy_process_group()
+    t.cancel()
+
+
 def main_ours(args):
     import torch
     import torch.distributed as dist
@@ -539,7 +558,7 @@ def main_ours(args):
 
     if rank != 0:
         if world > 1:
-            dist.destroy_process_group()
+            _leave_process_group(torch, dist, [ENV[0]])
         return 0
 
     # ---- roofline of the dominant kernel ------------------------------------------------------
@@ -679,9 +698,9 @@ def main_ours(args):
                 gpu_launches=launches, roofline=roofline, cpu_baseline=cpu_baseline, gpu_eager_baseline=gpu_eager,
                 small_field=small, culled=culled, fwd_f16x3=f16x3, strong_scaling=strong)
     line["uncached" if cached else "cached"] = other
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        _leave_process_group(torch, dist, [ENV[0]])
     return 0
 
 

@@ -42,7 +42,7 @@ class Scene(C.Structure):
 class Feed(C.Structure):
     """helio_feed_t (include/helio_b200.h): encoder-feed outputs of the splat epilogue."""
     _fields_ = [("img2", C.c_void_p), ("img2_batch_stride", C.c_int64), ("eps", C.c_float), ("com_coords", C.c_void_p),
-                ("com_sums", C.c_void_p), ("partials", C.c_void_p)]
+                ("com_sums", C.c_void_p), ("partials", C.c_void_p), ("partials_floats", C.c_int64)]
 
 
 class HelioLibError(RuntimeError):

@@ -312,6 +312,8 @@ int splat_fwd_feed_impl(const float* params, int B, int N, int R, float width, f
     const DeviceInfo* d = nullptr;
     if (int rc = require_device(&d)) return rc;
     if (splat_fwd_uses_tc(impl, B, N, R) && feed->partials != nullptr) {
+        if (feed->partials_floats < (int64_t)B * splat_tc_fwd_partials_per_image(R, d->sms, tc_pair_mode()) * 3)
+            return set_error(HELIO_E_WORKSPACE, "feed partials buffer too small%s%s");
         FwdFuse fz{};
         fz.partials = feed->partials, fz.img2 = feed->img2, fz.img2_bstride = (long long)feed->img2_batch_stride;
         if (int rc = splat_fwd_impl(params, B, N, R, width, height, img, impl, stream, kFuseFeed, fz, counts)) return rc;

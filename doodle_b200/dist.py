@@ -104,6 +104,9 @@ def make_sharded_env(env_cls, *args, global_batch_size: int, rank: Optional[int]
     concatenating the ranks reproduces the single-process environment exactly, draw for draw.  ``ref_min`` / ``ref_max``
     are all-reduced (min / max) in ``set_sun_pos``.  Metrics returned by ``step`` are the global means (one packed
     all-reduce); gradients w.r.t. the local actions are those of the global means.
+
+    Small fields replay CUDA graphs that contain the NCCL all-reduce (``graph="auto"``): call ``env.close()`` before
+    ``torch.distributed.destroy_process_group()``.
     """
     rank = dist.get_rank(group) if rank is None else rank
     world_size = dist.get_world_size(group) if world_size is None else world_size
@@ -130,6 +133,10 @@ def make_sharded_env(env_cls, *args, global_batch_size: int, rank: Optional[int]
 
         def _reduce_minmax(self, mn, mx):
             return all_reduce_minmax(mn, mx, group)
+
+        # transparent graph replay (graphs.StepGraph): the packed all-reduce is captured INTO the forward graph (NCCL
+        # collectives are capturable), so a sharded small field replays one graph per step like the single-process env
+        _graph_reduce = (group, world_size)
 
     if seed is not None:
         torch.manual_seed(seed)

@@ -377,6 +377,16 @@ class HelioEnv(_EnvBase):
                 assert not math.isinf(dist_l), "Distance loss is Inf"
                 assert not math.isinf(bound), "Boundary loss is Inf"
 
+    def close(self):
+        """Raise pending asserts and release the captured CUDA graphs (and the static buffers they own).  A sharded env
+        whose graphs captured the NCCL all-reduce must be closed before ``torch.distributed.destroy_process_group()``:
+        destroying a communicator while graphs that captured its kernels are alive hangs."""
+        try:
+            self._check_deferred()
+        finally:
+            self._step_graph = None
+            self._graph_warm = 0
+
     def flush_checks(self):
         """Raise any pending NaN/Inf assert now (waits for the last step's forward)."""
         self._check_deferred()
@@ -397,8 +407,8 @@ class HelioEnv(_EnvBase):
         if not (isinstance(action, torch.Tensor) and action.is_cuda):
             return False
         cls = type(self)
-        if cls._reduce_means is not HelioEnv._reduce_means or cls._quantile_cutoff is not HelioEnv._quantile_cutoff:
-            return False                                # sharded env: the metric all-reduce is not part of the graph
+        if cls._reduce_means is not HelioEnv._reduce_means and not self._graph_reduce_ok():
+            return False                                # a reduction hook the graph cannot reproduce
         if self.graph == "auto":
             B, N, R = self.batch_size, self.num_heliostats, self.resolution
             if B * N * R * R > (1 << 33) or B * R * R > (1 << 26):
@@ -408,6 +418,15 @@ class HelioEnv(_EnvBase):
                 return False
         # a caller capturing its own graph, or timing kernels with helio_profile_*, gets the eager kernels
         return not profiling() and not torch.cuda.is_current_stream_capturing()
+
+    def _graph_reduce_ok(self) -> bool:
+        """Sharded env (dist.make_sharded_env): its packed all-reduce can be captured into the forward graph when the
+        process group runs on NCCL (a gloo group lives on the host and cannot)."""
+        spec = getattr(self, "_graph_reduce", None)
+        if spec is None:
+            return False
+        import torch.distributed as dist
+        return dist.is_available() and dist.is_initialized() and dist.get_backend(spec[0]) == "nccl"
 
     def _graph_step(self, action):
         nf = self.noisy_field

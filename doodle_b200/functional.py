@@ -364,7 +364,7 @@ class StepFn(torch.autograd.Function):
             nfl = int(lib.helio_step_partials_floats(B, N, R, impl))
             if nfl > 0:
                 feed_partials = torch.empty(nfl, **f32)
-                feed.partials = feed_partials.data_ptr()
+                feed.partials, feed.partials_floats = feed_partials.data_ptr(), nfl
         with _Call("step_fwd", dev):
             rc = lib.helio_step_fwd_feed(
                 C.byref(scene), _ptr(helio), _ptr(sun), _ptr(action), _ptr(errs), _ptr(dmaps), B, N, R, impl,

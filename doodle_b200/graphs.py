@@ -76,12 +76,16 @@ class StepGraph:
         self.target = torch.empty(B, R, R, **f32)
         self.tx = torch.empty(B, **f32)
         self.helio = nf.heliostat_positions
-        self.inv_counts = env._inv_counts
+        # sharded env: the packed sums are all-reduced inside the forward graph and divided by the GLOBAL counts
+        # (dist.global_means); the backward of that all-reduce is the identity, so d means / d packed_local is the same factor
+        self.reduce = getattr(env, "_graph_reduce", None)          # (process group, world size): only dist.make_sharded_env sets it
+        self.inv_counts = env._inv_counts if self.reduce is None else env._inv_counts / self.reduce[1]
         self.scene = nf.scene()
         self.workspace = torch.zeros_like(nf._geom_workspace(B))
         self.src_keys = {}                                      # (data_ptr, version) of the env tensors last copied in
         self.sun_gen = 0
         # backward statics
+        self.reduced = torch.zeros(4, **f32)
         self.g_means = torch.zeros(4, **f32)
         self.g_packed = torch.zeros(4, **f32)
         self.g_per_img = torch.zeros(B, 3, **f32)
@@ -177,7 +181,13 @@ class StepGraph:
             _ptr(self.workspace), self.workspace.numel() * 4, _stream())
         _lib.check(rc, "helio_step_fwd")
         # the glue HelioEnv.step performs in torch, same ops (bit-identical): means, mae_image, aux
-        torch.mul(s["packed"], self.inv_counts, out=s["means"])
+        if self.reduce is not None:
+            import torch.distributed as dist
+            self.reduced.copy_(s["packed"])             # keep the local sums in the arena (they are this rank's outputs)
+            dist.all_reduce(self.reduced, op=dist.ReduceOp.SUM, group=self.reduce[0])
+            torch.mul(self.reduced, self.inv_counts, out=s["means"])
+        else:
+            torch.mul(s["packed"], self.inv_counts, out=s["means"])
         torch.div(s["per_img"][:, 2:3], float(R * R), out=s["mae"])
         s["aux"][:, :3].copy_(self.sun)
         s["aux"][:, 3:].copy_(s["action"].view(B, 3 * N))

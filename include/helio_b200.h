@@ -261,6 +261,7 @@ typedef struct helio_feed {
     float* com_coords;      /* [B][2], may be NULL together with com_sums */
     float* com_sums;        /* [B][3] */
     float* partials;
+    int64_t partials_floats; /* floats available at `partials` (HELIO_E_WORKSPACE if fewer than helio_step_partials_floats) */
 } helio_feed_t;
 
 /* helio_splat_fwd with the feed outputs (K2 + centre of mass + optional second image copy in one kernel). */

@@ -58,5 +58,47 @@ for (N, R, B, mask) in [(40, 64, 8 * world, False), (300, 256, 4 * world, False)
         print(f"N={N} R={R} B={B} mask={mask} world={world}: images equal {img_ok}, metrics {met_ok}, grad rel err {gerr:.2e} -> "
               f"{'ok' if flag.item() == 1 else 'MISMATCH'}", flush=True)
     ok = ok and flag.item() == 1
+# transparent graph replay on the sharded env: the packed all-reduce is captured into the forward graph (NCCL); several steps,
+# two of them alive at once, against the eager single-process env
+N, R, B = 50, 128, 8 * world
+g = torch.Generator().manual_seed(6)
+helio = torch.rand(N, 3, generator=g) * 10 + 80; helio[:, 2] = 0
+kw = dict(heliostat_pos=helio.to(dev), targ_pos=torch.tensor([0., -5., 0.], device=dev), targ_area=(15., 15.),
+          targ_norm=torch.tensor([0., 1., 0.], device=dev), sigma_scale=0.05, error_scale_mrad=90.0, resolution=R, device=str(dev))
+env = make_sharded_env(HelioEnv, global_batch_size=B, seed=321, graph=True, **kw)
+torch.manual_seed(321)
+full = HelioEnv(batch_size=B, graph=False, **kw)
+lo, hi = shard_bounds(B, rank, world)
+good = True
+for rep in range(3):
+    torch.manual_seed(50 + rep); env.reset()
+    torch.manual_seed(50 + rep); full.reset()
+    torch.manual_seed(9 + rep)
+    acts = [torch.nn.functional.normalize(full.ideal_normals + 0.02 * torch.randn(B, N, 3, device=dev), dim=2) for _ in range(2)]
+    la, lf, leaves_a, leaves_f = [], [], [], []
+    for a in acts:
+        al = a[lo:hi].clone().requires_grad_(True); af = a.clone().requires_grad_(True)
+        _, ml, _ = env.step(al); _, mf, _ = full.step(af)
+        la.append(ml["mse"] + 0.01 * ml["dist"] + ml["bound"] + ml["alignment_loss"]); lf.append(mf["mse"] + 0.01 * mf["dist"] + mf["bound"] + mf["alignment_loss"])
+        leaves_a.append(al); leaves_f.append(af)
+    sum(la).backward(); sum(lf).backward()
+    for k in range(2):
+        met_ok = abs(float(la[k]) - float(lf[k])) <= 2e-5 * abs(float(lf[k]))
+        gerr = float((leaves_a[k].grad - leaves_f[k].grad[lo:hi]).abs().max() / leaves_f[k].grad.abs().max())
+        good = good and met_ok and gerr < 1e-5
+replayed = env._step_graph is not None
+flag = torch.tensor([1.0 if (good and replayed) else 0.0], device=dev)
+dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+if rank == 0:
+    print(f"sharded graph replay N={N} R={R} B={B} world={world}: replayed {replayed}, parity {good} -> {'ok' if flag.item() == 1 else 'MISMATCH'}", flush=True)
+ok = ok and flag.item() == 1
+env.close()                       # graphs that captured NCCL kernels must go before the communicator does
+del env, full
+import gc, threading
+gc.collect()
+torch.cuda.synchronize()
+code = 0 if ok else 1
+t = threading.Timer(30.0, lambda: os._exit(code)); t.daemon = True; t.start()      # never let a teardown hang cost GPU time
 dist.destroy_process_group()
-sys.exit(0 if ok else 1)
+sys.stdout.flush()
+os._exit(code)

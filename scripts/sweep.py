@@ -104,11 +104,17 @@ def main():
             line["speedup_vs_cpu_port"] = round(line["evals_per_s"] / cpu_cache[(N, R)][0], 1)
         if rank == 0:
             print(json.dumps(line), flush=True)
+        env.close()                                   # release captured graphs (they may hold NCCL kernels) before the next point
         del env, action0
         torch.cuda.empty_cache()
         torch.cuda.reset_peak_memory_stats()
     if world > 1:
+        import threading
+        torch.cuda.synchronize()
+        t = threading.Timer(30.0, lambda: os._exit(0)); t.daemon = True; t.start()      # never let a teardown hang cost GPU time
         dist.destroy_process_group()
+        sys.stdout.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":
