@@ -57,6 +57,7 @@ def parse():
                     help="headline = target re-rendered every step as the reference does (default: exact target cache, the product default)")
     ap.add_argument("--no-gpu-eager", action="store_true", help="skip the torch-eager dense comparator on the same GPU")
     ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling block (N > 1)")
+    ap.add_argument("--no-both-3xtf32", action="store_true", help="skip the side measurement with both contractions in 3xTF32")
     ap.add_argument("--e2e-serial", action="store_true", help="e2e arm with caller-side copies instead of the host-action step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-culled", action="store_true", help="skip the opt-in footprint-culling side measurement")
@@ -574,9 +575,16 @@ def main_ours(args):
         pass
     bf16 = float(peaks.get("bf16_tflops_sustained") or peaks.get("bf16_tflops") or 1400.0)
     bf16_burst = float(peaks.get("bf16_tflops") or bf16)
-    peak = bf16 / 2.0 / 3.0
     tf32 = measure_tf32_peak(torch)
     dom = max(("splat_fwd", "splat_bwd"), key=lambda k: kprof.get(k, {}).get("total_ms", 0.0))
+    # operand format of the dominant kernel: "3xtf32" (three kind::tf32 MMAs per MAC, peak = TF32 dense / 3 = bf16 / 6) or
+    # "f16x3" (three kind::f16 MMAs per MAC at twice the rate, peak = bf16 dense / 3); same 22-bit operand accuracy
+    fwd_mode = int(os.environ.get("HELIO_FWD_PREC", "2"))
+    bwd_mode = int(os.environ.get("HELIO_BWD_PREC", str(_lib.BWD_PREC_DEFAULT)))
+    fmt = {"splat_fwd": "f16x3" if fwd_mode in (1, 2) else "3xtf32",
+           "splat_bwd": "f16x3" if bwd_mode == 1 else "3xtf32"}
+    per_mac = 3.0 if fmt[dom] == "f16x3" else 6.0           # bf16-dense FLOP spent per algorithmic FLOP
+    peak = bf16 / per_mac
     d = kprof.get(dom, {})
     avg_ms = d.get("avg_ms") or float("nan")
     flops_launch = FLOP_PER_EVAL[dom] * float(B) * N * R * R
@@ -594,20 +602,23 @@ def main_ours(args):
     # stage, the backward pads the heliostat rows of a tile to 128 per CTA (256 per CTA pair at R > 128)
     pad = ((N + 31) // 32 * 32) / float(N) if dom == "splat_fwd" else ((N + 255) // 256 * 256 if R > 128 else (N + 127) // 128 * 128) / float(N)
     executed = 3.0 * flops_launch * pad
-    pipe_frac = executed / (avg_ms * 1e-3) / (n_sms * 4096.0 * sm_mhz * 1e6)
+    pipe_rate = 8192.0 if fmt[dom] == "f16x3" else 4096.0   # tensor FLOP / clk / SM of the MMA kind in use
+    pipe_frac = executed / (avg_ms * 1e-3) / (n_sms * pipe_rate * sm_mhz * 1e6)
     mhz_dom = mhz_fwd if dom == "splat_fwd" else mhz_bwd
-    pipe_frac_held = executed / (avg_ms * 1e-3) / (n_sms * 4096.0 * mhz_dom * 1e6) if mhz_dom else None
+    pipe_frac_held = executed / (avg_ms * 1e-3) / (n_sms * pipe_rate * mhz_dom * 1e6) if mhz_dom else None
     roofline = dict(bound="tensor", kernel=dom, achieved=achieved, peak=peak, unit="TFLOP/s", frac=achieved / peak, traffic=traffic,
-                    peak_source=f"{peak_src}: bf16 {bf16:.0f} TFLOP/s sustained / 2 (TF32) / 3 (3xTF32)",
-                    frac_of_burst_peak=achieved / (bf16_burst / 6.0), burst_peak=bf16_burst / 6.0,
+                    operand_format=fmt,
+                    peak_source=f"{peak_src}: bf16 {bf16:.0f} TFLOP/s sustained / " + ("3 (f16x3: three kind::f16 MMAs per MAC)" if fmt[dom] == "f16x3"
+                                                                                       else "2 (TF32) / 3 (3xTF32)"),
+                    frac_of_burst_peak=achieved / (bf16_burst / per_mac), burst_peak=bf16_burst / per_mac,
                     tensor_pipe_frac=pipe_frac,
                     sm_mhz_held_in_kernel=dict(splat_fwd=mhz_fwd, splat_bwd=mhz_bwd,
                                                note="cycles / nanoseconds measured INSIDE the tcgen05 kernels (helio_tc_clock_mhz): B200 power-throttles under "
                                                     "sustained tensor load while NVML keeps reporting the application clock"),
                     tensor_pipe_frac_at_held_clock=pipe_frac_held,
-                    tensor_pipe_note=f"executed tcgen05 FLOP (3 x algorithmic x K padding) / ({n_sms} SMs x 4096 TF32 FLOP/clk x {sm_mhz:.0f} MHz median under load)",
+                    tensor_pipe_note=f"executed tcgen05 FLOP (3 x algorithmic x padding) / ({n_sms} SMs x {pipe_rate:.0f} FLOP/clk ({fmt[dom]}) x {sm_mhz:.0f} MHz median under load)",
                     cublas_tf32_inrun_tflops=tf32, frac_of_cublas_tf32_over_3=achieved / (tf32 / 3.0),
-                    frac_of_nominal_tf32_over_3=achieved / (1125.0 / 3.0),   # 2.25 PFLOP/s bf16 nominal / 2 / 3
+                    frac_of_nominal_peak=achieved / (2250.0 / per_mac),   # 2.25 PFLOP/s bf16 nominal dense
                     avg_launch_ms=avg_ms, share_of_step=d.get("total_ms", 0.0) / ms_total if ms_total else None,
                     kernels_ms={k: round(v["avg_ms"], 4) for k, v in sorted(kprof.items())},
                     launches_per_step={k: v["n"] / steps for k, v in sorted(kprof.items())},
@@ -615,8 +626,8 @@ def main_ours(args):
                          + ", ".join(f"{k} {FLOP_PER_EVAL[k] * float(B) * N * R * R / (kprof[k]['avg_ms'] * 1e-3) / 1e12:.0f} TFLOP/s"
                                      for k in ("splat_fwd", "splat_bwd") if k != dom and k in kprof)
                          + "; traffic = dram read+write bytes per launch from profiles/ (ncu --set full); frac > 1 is possible against the sustained "
-                           "figure because MEASURED_PEAKS.json took it power-throttled (1335 MHz) while this kernel holds ~1.9 GHz: "
-                           "frac_of_burst_peak and tensor_pipe_frac are the informative ones")
+                           "figure because MEASURED_PEAKS.json took it power-throttled (1335 MHz): frac_of_burst_peak and "
+                           "tensor_pipe_frac_at_held_clock are the informative ones")
 
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:      # reported at N=1 only
@@ -654,24 +665,27 @@ def main_ours(args):
             culled = dict(error=repr(e))
         finally:
             env.cull = False
-    # ---- opt-in f16x3 forward operands (secondary; the headline above is 3xTF32 in both directions) ----
-    f16x3 = None
-    if not args.no_culled and world == 1:
+    # ---- both contractions in 3xTF32 (the format BASELINE.json names; the backward's default is f16x3) ----
+    tf32x3 = None
+    if not args.no_both_3xtf32 and world == 1:
         try:
-            _lib.check(_lib.load().helio_set_fwd_precision(1), "helio_set_fwd_precision")
+            _lib.check(_lib.load().helio_set_bwd_precision(0), "helio_set_bwd_precision")
+            _lib.check(_lib.load().helio_set_fwd_precision(0), "helio_set_fwd_precision")
             for _ in range(3):
                 one_step(action0)
             Fn.reset_profile(True)
-            ms_h = timed(lambda: one_step(action0), steps) / steps
-            kh = Fn.collect_profile()
+            ms_t = timed(lambda: one_step(action0), steps) / steps
+            kt = Fn.collect_profile()
             Fn.reset_profile(False)
-            f16x3 = dict(ms_per_step=ms_h, evals_per_s=evals_step / (ms_h * 1e-3), kernels_ms={k: round(v["avg_ms"], 4) for k, v in sorted(kh.items())},
-                         note="helio_set_fwd_precision(1): forward operands as two fp16 pieces of the 2^14-scaled Gaussians (3 kind::f16 MMAs per "
-                              "K-step, fp32 accumulate); measured error vs fp64 is not larger than 3xTF32's (tests/test_gpu_parity.py); backward stays 3xTF32")
+            tf32x3 = dict(ms_per_step=ms_t, evals_per_s=evals_step / (ms_t * 1e-3), kernels_ms={k: round(v["avg_ms"], 4) for k, v in sorted(kt.items())},
+                          note="helio_set_fwd_precision(0) + helio_set_bwd_precision(0): both contractions in 3xTF32, the format BASELINE.json "
+                               "names (the defaults are the f16x3 formats: same 22-bit operand accuracy, half the tensor work); same "
+                               "results within the parity tolerances")
         except Exception as e:
-            f16x3 = dict(error=repr(e))
+            tf32x3 = dict(error=repr(e))
         finally:
-            _lib.load().helio_set_fwd_precision(2)     # default: auto (f16x3 up to R = 128, 3xTF32 above)
+            _lib.load().helio_set_bwd_precision(bwd_mode)
+            _lib.load().helio_set_fwd_precision(2)
     small = None
     if world == 1 and not args.no_small_field:
         try:
@@ -696,7 +710,7 @@ def main_ours(args):
                                         cpus_allowed=len(os.sched_getaffinity(0)),
                                         note="pinned 98 MB copies issued by all ranks at once, slowest rank")),
                 gpu_launches=launches, roofline=roofline, cpu_baseline=cpu_baseline, gpu_eager_baseline=gpu_eager,
-                small_field=small, culled=culled, fwd_f16x3=f16x3, strong_scaling=strong)
+                small_field=small, culled=culled, both_3xtf32=tf32x3, strong_scaling=strong)
     line["uncached" if cached else "cached"] = other
     print(json.dumps(line), flush=True)
     if world > 1:

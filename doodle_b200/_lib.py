@@ -16,9 +16,10 @@ CSRC = os.path.join(_HERE, "csrc")
 ABI_VERSION = 5
 
 SPLAT_AUTO, SPLAT_SIMT, SPLAT_TC = 0, 1, 2
+BWD_PREC_DEFAULT = 1     # helio_set_bwd_precision: 1 = f16x3 (K = 64 per stage) inside helio_step_bwd, 0 = 3xTF32
 
 EXPORTS = (
-    "helio_abi_version", "helio_last_error", "helio_device_ok", "helio_set_tc_pair_mode", "helio_set_fwd_precision", "helio_geom_workspace_bytes", "helio_geom_fwd",
+    "helio_abi_version", "helio_last_error", "helio_device_ok", "helio_set_tc_pair_mode", "helio_set_fwd_precision", "helio_set_bwd_precision", "helio_geom_workspace_bytes", "helio_geom_fwd",
     "helio_geom_bwd", "helio_splat_fwd", "helio_splat_bwd", "helio_image_max", "helio_loss_fwd", "helio_loss_bwd",
     "helio_profile_enable", "helio_profile_count", "helio_profile_get",
     "helio_distance_maps_workspace_bytes", "helio_distance_maps",
@@ -76,6 +77,8 @@ def _declare(lib):
     lib.helio_set_tc_pair_mode.argtypes = [i]
     lib.helio_set_fwd_precision.restype = i
     lib.helio_set_fwd_precision.argtypes = [i]
+    lib.helio_set_bwd_precision.restype = i
+    lib.helio_set_bwd_precision.argtypes = [i]
     lib.helio_profile_enable.restype = i
     lib.helio_profile_enable.argtypes = [i]
     lib.helio_profile_count.restype = i

@@ -14,6 +14,10 @@
 
 using namespace helio;
 
+#ifndef HELIO_BWD_PREC_DEFAULT
+#define HELIO_BWD_PREC_DEFAULT 1
+#endif
+
 namespace {
 
 struct DeviceInfo {
@@ -65,11 +69,10 @@ std::atomic<int>& tc_pair_state() {
 int tc_pair_mode() { return tc_pair_state().load(std::memory_order_relaxed); }
 
 // forward splat operand format: 0 = 3xTF32 everywhere, 1 = f16x3 everywhere (two fp16 pieces of the 2^14-scaled Gaussians),
-// 2 = auto (default): f16x3 for images up to 128 pixels a side, 3xTF32 above.  Both carry 22 significant bits per operand;
-// measured error against fp64 of f16x3 is not larger than 3xTF32's at any tested shape (test_forward_f16x3_...).  At
-// R <= 128 a CTA generates as many operand rows per stage as at R = 256 for half (a quarter) of the MMAs, so the kernel is
-// bound by operand generation and the cheaper MMAs / half-size stages of f16x3 pay (-3 ... -12 % measured); at R = 256 the
-// headline configuration keeps the 3xTF32 contraction BASELINE.json names.
+// 2 = auto (default) = f16x3.  Both carry 22 significant bits per operand; measured error against fp64 of f16x3 is not
+// larger than 3xTF32's at any tested shape (test_forward_f16x3_...), it halves the tensor work (the B200 is power-limited
+// inside these kernels) and its half-size stages deepen the ring: forward -3 ... -12 % at R <= 128, -10 ... -14 % at R = 256.
+// 3xTF32 -- the format BASELINE.json names -- stays selectable (mode 0) and is what bench.py reports as `both_3xtf32`.
 std::atomic<int>& fwd_prec_state() {
     static std::atomic<int> mode{[]() {
         const char* e = std::getenv("HELIO_FWD_PREC");
@@ -78,9 +81,21 @@ std::atomic<int>& fwd_prec_state() {
     }()};
     return mode;
 }
+// backward splat operand format inside helio_step_bwd: 0 = 3xTF32, 1 = f16x3 with K = 64 per stage (see SplatBwdTc).
+// The f16x3 backward needs the per-image maximum of |dL/dimg|, which the loss backward produces on the way; the standalone
+// helio_splat_bwd (arbitrary g_img, no scratch) always uses 3xTF32.
+std::atomic<int>& bwd_prec_state() {
+    static std::atomic<int> mode{[]() {
+        const char* e = std::getenv("HELIO_BWD_PREC");
+        const int v = e ? std::atoi(e) : HELIO_BWD_PREC_DEFAULT;
+        return (v == 0 || v == 1) ? v : HELIO_BWD_PREC_DEFAULT;
+    }()};
+    return mode;
+}
 int fwd_prec_for(int R) {
     const int m = fwd_prec_state().load(std::memory_order_relaxed);
-    return m == 2 ? (R <= 128 ? 1 : 0) : m;
+    (void)R;
+    return m == 2 ? 1 : m;
 }
 
 // ---- opt-in per-kernel timing (helio_profile_*): CUDA events recorded around every kernel this library
@@ -165,8 +180,17 @@ HELIO_API int helio_profile_get(int index, const char** name, float* ms) {
 }
 
 #if HELIO_TC_STATS
+namespace {
+int splat_bwd_impl(const float* params, const float* g_img, int B, int N, int R, float width, float height, float* moments,
+                   int impl, void* stream, const int* counts, const int* index, const float* gmax);
+}
+// debug builds only: the f16x3 backward splat on its own (gmax[B] = per-image max |g_img|, computed by the caller)
+HELIO_API int helio_debug_splat_bwd_f16(const float* params, const float* g_img, const float* gmax, int B, int N, int R, float width,
+                                        float height, float* moments, void* stream) {
+    return splat_bwd_impl(params, g_img, B, N, R, width, height, moments, HELIO_SPLAT_TC, stream, nullptr, nullptr, gmax);
+}
 // debug builds only (-DHELIO_TC_STATS=1, scripts/tc_stats.py): copy out / clear the per-warp cycle counters of the last
-// tcgen05 kernel.  out: [160][16][4] uint64.
+// tcgen05 kernel.  out: [160][24][4] uint64.
 HELIO_API int helio_debug_tc_stats(unsigned long long* out_host, int clear) {
     HELIO_CUDA_OK(cudaDeviceSynchronize());
     if (out_host) HELIO_CUDA_OK(cudaMemcpyFromSymbol(out_host, g_tc_stats, sizeof(g_tc_stats)));
@@ -184,6 +208,12 @@ HELIO_API int helio_tc_clock_mhz(int which, float* mhz_host) {
     unsigned long long v[2][2];
     HELIO_CUDA_OK(cudaMemcpyFromSymbol(v, g_tc_clock, sizeof(v)));     // synchronises with the device
     *mhz_host = v[which][1] ? (float)((double)v[which][0] * 1e3 / (double)v[which][1]) : 0.f;
+    return 0;
+}
+
+HELIO_API int helio_set_bwd_precision(int mode) {
+    if (mode != 0 && mode != 1) return set_error(HELIO_E_BADARG, "bad argument: %s%s", "backward precision mode must be 0 or 1");
+    bwd_prec_state().store(mode, std::memory_order_relaxed);
     return 0;
 }
 
@@ -276,7 +306,7 @@ bool splat_bwd_uses_tc(int impl, int B, int N, int R) {
 }
 
 int splat_bwd_impl(const float* params, const float* g_img, int B, int N, int R, float width, float height, float* moments,
-                   int impl, void* stream, const int* counts = nullptr, const int* index = nullptr) {
+                   int impl, void* stream, const int* counts = nullptr, const int* index = nullptr, const float* gmax = nullptr) {
     const DeviceInfo* d = nullptr;
     if (int rc = require_device(&d)) return rc;
     HELIO_REQUIRE(params && g_img && moments, "null pointer");
@@ -288,7 +318,7 @@ int splat_bwd_impl(const float* params, const float* g_img, int B, int N, int R,
     if (splat_bwd_uses_tc(impl, B, N, R)) {
         if (counts) HELIO_CUDA_OK(cudaMemsetAsync(moments, 0, (size_t)B * N * 16, (cudaStream_t)stream));   // culled heliostats: zero
         HELIO_CUDA_OK(splat_tc_bwd(params, g_img, moments, B, N, R, width, height, d->sms, (cudaStream_t)stream, tc_pair_mode(),
-                                   counts, index));
+                                   counts, index, gmax));
     } else {
         HELIO_REQUIRE(counts == nullptr, "culled input needs the tcgen05 path");
         HELIO_CUDA_OK(splat_bwd_simt(params, g_img, moments, B, N, R, width, height, d->sms, (cudaStream_t)stream));
@@ -437,9 +467,20 @@ HELIO_API int helio_loss_bwd(const float* img, const float* target, const float*
     return helio_loss_bwd_packed(img, target, dmaps, tx, g_per_img, nullptr, g_img_in, B, R, g_img, stream);
 }
 
+namespace {
+int loss_bwd_impl(const float* img, const float* target, const float* dmaps, const float* tx, const float* g_per_img,
+                  const float* g_packed, const float* g_img_in, int B, int R, float* g_img, float* gmax, void* stream);
+}
+
 HELIO_API int helio_loss_bwd_packed(const float* img, const float* target, const float* dmaps, const float* tx,
                           const float* g_per_img, const float* g_packed, const float* g_img_in, int B, int R, float* g_img,
                           void* stream) {
+    return loss_bwd_impl(img, target, dmaps, tx, g_per_img, g_packed, g_img_in, B, R, g_img, nullptr, stream);
+}
+
+namespace {
+int loss_bwd_impl(const float* img, const float* target, const float* dmaps, const float* tx, const float* g_per_img,
+                  const float* g_packed, const float* g_img_in, int B, int R, float* g_img, float* gmax, void* stream) {
     const DeviceInfo* d = nullptr;
     if (int rc = require_device(&d)) return rc;
     HELIO_REQUIRE(img && target && dmaps && tx && (g_per_img || g_packed) && g_img, "null pointer");
@@ -451,11 +492,16 @@ HELIO_API int helio_loss_bwd_packed(const float* img, const float* target, const
     if (slices > want) slices = want;
     if (slices < 1) slices = 1;
     KernelTimer timer("loss_bwd", stream);
+    if (gmax) {
+        fill_kernel<<<(B + 255) / 256, 256, 0, (cudaStream_t)stream>>>(gmax, B, 0.f);
+        HELIO_CUDA_OK(cudaGetLastError());
+    }
     loss_bwd_kernel<<<(unsigned)((long long)B * slices), kLossThreads, 0, (cudaStream_t)stream>>>(
-        img, target, dmaps, tx, g_per_img, g_packed, g_img_in, R, slices, g_img);
+        img, target, dmaps, tx, g_per_img, g_packed, g_img_in, R, slices, g_img, gmax);
     HELIO_CUDA_OK(cudaGetLastError());
     return 0;
 }
+}  // namespace
 
 HELIO_API int helio_loss_pack(const float* per_img, int B, float* packed, void* stream) {
     const DeviceInfo* d = nullptr;
@@ -600,9 +646,12 @@ HELIO_API int helio_step_bwd(const helio_scene_t* scene, const float* helio_pos,
     HELIO_REQUIRE(moments || !(g_packed || g_per_img || g_img_in), "moments scratch missing");
     const float* g_mom = nullptr;
     if (g_packed || g_per_img) {
-        HELIO_REQUIRE(g_img, "g_img scratch missing");
-        if (int rc = helio_loss_bwd_packed(img, target, dmaps, tx, g_per_img, g_packed, g_img_in, B, R, g_img, stream)) return rc;
-        if (int rc = splat_bwd_impl(sp, g_img, B, N, R, scene->width, scene->height, moments, impl, stream, counts, index)) return rc;
+        HELIO_REQUIRE(g_img && g_action, "g_img scratch missing");
+        // f16x3 backward: the loss backward also leaves max |g_img[b]| per image, in the first B floats of g_action -- free
+        // until the geometry adjoint, the last kernel of this call, overwrites the whole buffer
+        float* gmax = (bwd_prec_state().load(std::memory_order_relaxed) == 1 && splat_bwd_uses_tc(impl, B, N, R)) ? g_action : nullptr;
+        if (int rc = loss_bwd_impl(img, target, dmaps, tx, g_per_img, g_packed, g_img_in, B, R, g_img, gmax, stream)) return rc;
+        if (int rc = splat_bwd_impl(sp, g_img, B, N, R, scene->width, scene->height, moments, impl, stream, counts, index, gmax)) return rc;
         g_mom = moments;
     } else if (g_img_in) {
         if (int rc = splat_bwd_impl(sp, g_img_in, B, N, R, scene->width, scene->height, moments, impl, stream, counts, index)) return rc;

@@ -230,10 +230,13 @@ com_pack_partials_kernel(const float* __restrict__ partials, int P, int B, float
 __global__ void __launch_bounds__(kLossThreads)
 loss_bwd_kernel(const float* __restrict__ img, const float* __restrict__ target, const float* __restrict__ dmaps,
                 const float* __restrict__ tx, const float* __restrict__ g_per_img, const float* __restrict__ g_packed,
-                const float* __restrict__ g_in, int R, int slices, float* __restrict__ g_img) {
+                const float* __restrict__ g_in, int R, int slices, float* __restrict__ g_img, float* __restrict__ gmax) {
+    // gmax (may be NULL): [B], zero-initialised by the caller; receives max |g_img[b]| (atomicMax on the int pattern of the
+    // non-negative values, order-free) -- the per-image power-of-two scale of K3's fp16-piece operands comes from it
     const int b = blockIdx.x / slices, s = blockIdx.x % slices;
     const size_t npix = (size_t)R * R, off = (size_t)b * npix;
     const float t = fmaxf(__ldg(tx + b), 1e-6f);
+    float mx = 0.f;
     float g0 = 0.f, g1 = 0.f, g2 = 0.f;
     if (g_per_img) g0 = __ldg(g_per_img + 3 * b), g1 = __ldg(g_per_img + 3 * b + 1), g2 = __ldg(g_per_img + 3 * b + 2);
     if (g_packed) g0 += __ldg(g_packed), g1 += __ldg(g_packed + 1);
@@ -251,11 +254,20 @@ loss_bwd_kernel(const float* __restrict__ img, const float* __restrict__ target,
         for (size_t i = (size_t)s * kLossThreads + threadIdx.x; i < npix / 4; i += (size_t)slices * kLossThreads) {
             const float4 p = __ldg(a + i), q = __ldg(c + i), w = __ldg(d + i);
             const float4 z = gi ? __ldg(gi + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-            o[i] = make_float4(one(p.x, q.x, w.x, z.x), one(p.y, q.y, w.y, z.y), one(p.z, q.z, w.z, z.z), one(p.w, q.w, w.w, z.w));
+            const float4 r = make_float4(one(p.x, q.x, w.x, z.x), one(p.y, q.y, w.y, z.y), one(p.z, q.z, w.z, z.z), one(p.w, q.w, w.w, z.w));
+            o[i] = r;
+            mx = fmaxf(fmaxf(mx, fmaxf(fabsf(r.x), fabsf(r.y))), fmaxf(fabsf(r.z), fabsf(r.w)));
         }
     } else {
-        for (size_t i = (size_t)s * kLossThreads + threadIdx.x; i < npix; i += (size_t)slices * kLossThreads)
-            g_img[off + i] = one(__ldg(img + off + i), __ldg(target + off + i), __ldg(dmaps + off + i), g_in ? __ldg(g_in + off + i) : 0.f);
+        for (size_t i = (size_t)s * kLossThreads + threadIdx.x; i < npix; i += (size_t)slices * kLossThreads) {
+            const float r = one(__ldg(img + off + i), __ldg(target + off + i), __ldg(dmaps + off + i), g_in ? __ldg(g_in + off + i) : 0.f);
+            g_img[off + i] = r;
+            mx = fmaxf(mx, fabsf(r));
+        }
+    }
+    if (gmax) {
+        mx = warp_max(mx);
+        if ((threadIdx.x & 31) == 0 && mx > 0.f) atomicMax(reinterpret_cast<int*>(gmax + b), __float_as_int(mx));
     }
 }
 

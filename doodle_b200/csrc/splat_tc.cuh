@@ -60,7 +60,7 @@ namespace helio {
 
 #if HELIO_TC_STATS
 // [CTA][warp][slot]: 0 = total cycles in the role loop, 1..3 = cycles blocked in the role's waits (see the kernels)
-__device__ unsigned long long g_tc_stats[160][16][4];
+__device__ unsigned long long g_tc_stats[160][24][4];
 __device__ __forceinline__ unsigned long long tc_clock() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%clock64;" : "=l"(t));
@@ -107,19 +107,30 @@ __device__ __forceinline__ unsigned long long probe_ns() {
 // ------------------------------------------------------------------------------------------------
 // pieces shared by both kernels
 // ------------------------------------------------------------------------------------------------
-template <int NT, int CG, int BROWS, int ASPLIT, int BSPLIT = 1, int TILES = 2, int EPI_BYTES = 0>
+template <int NT, int CG, int BROWS, int ASPLIT, int BSPLIT = 1, int TILES = 2, int EPI_BYTES = 0, int KC = 32, int F16PIECES = 0,
+          int BALT = 1, int ESPLIT = 1>
 struct SplatTcLayout {
     static constexpr int kNT = NT;                       // UMMA N (accumulator columns)
     static constexpr int kM = 128;                       // A rows per CTA = TMEM lanes
     static constexpr int kBRows = BROWS;                 // B operand rows produced by each CTA (NT / CG)
-    static constexpr int kKC = 32;                       // K per stage (one 128-byte swizzle row of tf32)
+    static constexpr int kKC = KC;                       // K per stage: 32 (one 128-byte swizzle row of tf32) or 64 (of fp16)
+    // F16PIECES = 1 (backward "f16x3", K = 64): the two tiles of an operand hold fp16 pieces p1 / p2 of 64 K values per
+    // 128-byte row instead of tf32 hi / lo of 32; same bytes, same descriptors, kind::f16 MMAs (K = 16 = 32 bytes per step)
+    static constexpr int kF16Pieces = F16PIECES;
+    static_assert(KC == 32 || (KC == 64 && F16PIECES == 1 && TILES == 2), "K per stage");
     static constexpr int kASplit = ASPLIT;               // warps sharing one 32-row slab of A (each takes kKC / ASPLIT of K)
     static constexpr int kAWarps = kM / 32 * ASPLIT;
     static constexpr int kBSplit = BSPLIT;               // same for the B operand rows
-    static constexpr int kBWarps = kBRows / 32 * BSPLIT;
+    // BALT groups of B-operand warps take the stages in turn (backward gradient stagers: a group then has BALT stage
+    // periods for the load latency of its tile instead of one); only one group arrives on a stage's full barrier
+    static constexpr int kBAlt = BALT;
+    static constexpr int kBWarps = kBRows / 32 * BSPLIT * BALT;
     static constexpr int kMmaWarp = kAWarps + kBWarps;
     static constexpr int kEpiWarp0 = kMmaWarp + 1;
-    static constexpr int kThreads = (kEpiWarp0 + 4) * 32;
+    // ESPLIT epilogue warps per TMEM lane quarter (each takes 1 / ESPLIT of an accumulator's columns; backward only)
+    static constexpr int kEpiSplit = ESPLIT;
+    static constexpr int kEpiWarps = 4 * ESPLIT;
+    static constexpr int kThreads = (kEpiWarp0 + kEpiWarps) * 32;
     static constexpr int kABytes = kM * 128;             // one of {hi, lo}
     static constexpr int kBBytes = kBRows * 128;
     // TILES = 2: {hi, lo} tf32 tiles per operand (3xTF32).  TILES = 1: one tile per operand whose 128-byte rows hold
@@ -134,8 +145,8 @@ struct SplatTcLayout {
     static constexpr int kFit = (227 * 1024 - kFixedBytes) / kStageBytes;
     static constexpr int kStages = kFit > (TILES == 1 ? 6 : 4) ? (TILES == 1 ? 6 : 4) : kFit;
     static constexpr int kSmemBytes = kStages * kStageBytes + kFixedBytes;
-    static constexpr int kFullCount = (kAWarps + kBWarps) * CG;   // one arrival per producer warp of the pair
-    static constexpr int kTEmptyCount = 4 * CG;                   // one arrival per epilogue warp of the pair
+    static constexpr int kFullCount = (kAWarps + kBWarps / BALT) * CG;   // one arrival per producer warp (of the group whose turn it is) of the pair
+    static constexpr int kTEmptyCount = kEpiWarps * CG;           // one arrival per epilogue warp of the pair
     static_assert(CG == 1 || CG == 2, "CTA group size");
     static_assert(BROWS * CG == NT, "each CTA of the group stages NT / CG rows of B");
     static_assert(kTmemCols <= 512 && (kTmemCols & (kTmemCols - 1)) == 0 && kTmemCols >= 32, "TMEM columns");
@@ -277,7 +288,7 @@ struct SplatTcCtx {
             }
             return;
         }
-        constexpr uint32_t idesc = tc::make_idesc_tf32(C::kM * CG, C::kNT);
+        constexpr uint32_t idesc = C::kF16Pieces ? tc::make_idesc_f16(C::kM * CG, C::kNT) : tc::make_idesc_tf32(C::kM * CG, C::kNT);
         const uint64_t a_hi = tc::make_desc_k_sw128(sa);
         const uint64_t a_lo = tc::make_desc_k_sw128(sa + C::kABytes);
         const uint64_t b_hi = tc::make_desc_k_sw128(sa + 2 * C::kABytes);
@@ -285,7 +296,17 @@ struct SplatTcCtx {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const uint64_t ko = (uint64_t)(k * 32 >> 4);   // +32 bytes per K step of 8 tf32
-            if constexpr (CG == 2) {
+            if constexpr (C::kF16Pieces) {           // p1 q1 + p1 q2 + p2 q1, 16 fp16 (32 bytes) of K per instruction
+                if constexpr (CG == 2) {
+                    tc::mma_f16_ss_2cta(d_tmem, a_hi + ko, b_hi + ko, idesc, !(first && k == 0));
+                    tc::mma_f16_ss_2cta(d_tmem, a_hi + ko, b_lo + ko, idesc, 1);
+                    tc::mma_f16_ss_2cta(d_tmem, a_lo + ko, b_hi + ko, idesc, 1);
+                } else {
+                    tc::mma_f16_ss(d_tmem, a_hi + ko, b_hi + ko, idesc, !(first && k == 0));
+                    tc::mma_f16_ss(d_tmem, a_hi + ko, b_lo + ko, idesc, 1);
+                    tc::mma_f16_ss(d_tmem, a_lo + ko, b_hi + ko, idesc, 1);
+                }
+            } else if constexpr (CG == 2) {
                 tc::mma_tf32_ss_2cta(d_tmem, a_hi + ko, b_hi + ko, idesc, !(first && k == 0));
 #ifndef HELIO_DEBUG_1XTF32   // timing experiment only: results are wrong without the cross terms
                 tc::mma_tf32_ss_2cta(d_tmem, a_hi + ko, b_lo + ko, idesc, 1);
@@ -828,15 +849,51 @@ inline cudaError_t splat_tc_fwd(const float* params, float* img, int B, int N, i
 //   product 1 (U): A rows = amp Gx[n, i-chunk]   B rows = g[i-chunk, j]^T (j = accumulator column)
 // The epilogue thread that owns TMEM lane n keeps {S0,Sx,Sxx} from product 0 in registers, adds
 // {Sy,Syy} from product 1 and writes one float4 per heliostat.
-template <int NT, int CG>
-using SplatBwdTc = SplatTcLayout<NT, CG, NT / CG, 2>;
+//
+// PREC = 1 ("f16x3", K = 64 per stage): the Gaussian operand lies in [0, 1] and is scaled by 2^14 as in the forward; the
+// image gradient is scaled PER IMAGE by the power of two that brings max |g[b]| just under 2^14 (gmax[b], produced by the
+// loss backward); both split into two fp16 pieces v = p1 + p2 (11 + 11 significant bits for every value within 2^-17 of the
+// image's maximum, absolute error below 2^-38 of that maximum for smaller ones).  An operand row of 64 K values is 128
+// bytes per piece -- the bytes a row of 32 tf32 values takes -- so a stage keeps its 64 KB, the ring its three stages and
+// the MMA issue its descriptors, but a stage now covers TWICE the contraction depth with the same 12 instructions
+// (kind::f16, K = 16): half the tensor work per eval, half the stage hand-overs, and the stagers' tile-load latency is
+// amortised over twice the data.  The epilogue unscales the moments by the exact power of two.
+#ifndef HELIO_BWD_PACKED2
+// 1: packed fp32x2 arithmetic (FADD2 / FMUL2 / FFMA2: the same IEEE operations, two results per instruction) in the backward
+// epilogue and in the f16x3 producers.  With 21 warps per SM the f16x3 backward is bound by instruction issue across its
+// roles (scripts/tc_stats.py), so halving the FP32 instruction count pays there (it did not in the latency-bound forward).
+#define HELIO_BWD_PACKED2 1
+#endif
+#ifndef HELIO_BWD_STAGER_GROUPS_F16
+#define HELIO_BWD_STAGER_GROUPS_F16 2    // f16x3 backward: two groups of gradient stagers take the stages in turn
+#endif
+#ifndef HELIO_BWD_STAGER_GROUPS
+#define HELIO_BWD_STAGER_GROUPS 1        // 3xTF32 backward
+#endif
+#ifndef HELIO_BWD_EPI_SPLIT_F16
+#define HELIO_BWD_EPI_SPLIT_F16 2        // f16x3 backward: two epilogue warps per TMEM lane quarter (half of the columns each)
+#endif
+template <int NT, int CG, int PREC = 0>
+using SplatBwdTc = SplatTcLayout<NT, CG, NT / CG, 2, 1, 2, (PREC && HELIO_BWD_EPI_SPLIT_F16 > 1) ? 4096 : 0, PREC ? 64 : 32, PREC,
+                                 // (the single-CTA 256-column variant already has eight stager warps: no second group, 25 warps)
+                                 PREC ? ((NT == 256 && CG == 1) ? 1 : HELIO_BWD_STAGER_GROUPS_F16) : HELIO_BWD_STAGER_GROUPS,
+                                 PREC ? HELIO_BWD_EPI_SPLIT_F16 : 1>;
 
-template <int NT, int CG>
-__global__ void __launch_bounds__(SplatBwdTc<NT, CG>::kThreads, 1)
+// exponent e with |v| < 2^(e+1) (v finite, > 0), else 0; and the power of two 2^k as a float
+__device__ __forceinline__ int float_exponent(float v) { return v > 0.f ? (int)((__float_as_uint(v) >> 23) & 0xFFu) - 127 : 0; }
+__device__ __forceinline__ float pow2i(int k) { return __uint_as_float((uint32_t)(min(max(k, -126), 127) + 127) << 23); }
+// per-image scale exponent of the gradient operand: |g| * 2^sexp < 2^14 (fp16 tops out at 65504)
+__device__ __forceinline__ int grad_scale_exponent(float gmax_b) {
+    return gmax_b > 0.f && gmax_b <= 3.0e38f ? min(max(13 - float_exponent(gmax_b), -100), 100) : 0;
+}
+
+template <int NT, int CG, int PREC>
+__global__ void __launch_bounds__(SplatBwdTc<NT, CG, PREC>::kThreads, 1)
 splat_bwd_tc_kernel(const float4* __restrict__ params, const int* __restrict__ counts, const int* __restrict__ index,
-                    const float* __restrict__ g_img, float4* __restrict__ moments, int N, int R, Axis ax, Axis ay, int nblocks,
-                    int num_tiles) {
-    using C = SplatBwdTc<NT, CG>;
+                    const float* __restrict__ g_img, const float* __restrict__ gmax, float4* __restrict__ moments, int N, int R,
+                    Axis ax, Axis ay, int nblocks, int num_tiles) {
+    using C = SplatBwdTc<NT, CG, PREC>;
+    static_assert(PREC == 0 || HELIO_BWD_DEFER == 0, "the f16x3 backward is written for the plain hand-off");
     extern __shared__ uint8_t smem_raw[];
     SplatTcCtx<C, CG> cx;
     cx.setup(smem_raw, R, ax, ay);
@@ -884,8 +941,8 @@ splat_bwd_tc_kernel(const float4* __restrict__ params, const int* __restrict__ c
 #pragma unroll 1
             for (int prod = 0; prod < 2; ++prod) {
                 const float ctr = prod == 0 ? p.y : p.x;
-                const float la = dead + (prod == 0 ? 0.f : log2f(p.w));       // amplitude folded into the exponent
-                const uint32_t tab = (prod == 0 ? cx.sY_u : cx.sX_u) + (uint32_t)q0 * 16u;
+                const float la = dead + (prod == 0 ? 0.f : log2f(p.w)) + (PREC == 1 ? 14.f : 0.f);   // amplitude (and the f16x3 scale 2^14) folded into the exponent
+                const uint32_t tab = (prod == 0 ? cx.sY_u : cx.sX_u) + (uint32_t)q0 * (PREC == 1 ? 32u : 16u);
 #pragma unroll 1
                 for (int pbk = 0; pbk < pblocks; ++pbk) {
 #pragma unroll 1
@@ -927,6 +984,37 @@ splat_bwd_tc_kernel(const float4* __restrict__ params, const int* __restrict__ c
                         }
                         const uint32_t hi_base = cx.smem_u + (uint32_t)(s * C::kStageBytes);
                         const uint32_t lo_base = hi_base + C::kABytes;
+                        if constexpr (PREC == 1) {
+                            // 16-byte chunk (q0 + q) of the row = 8 fp16 = K values k0 + 8 (q0 + q) .. + 7
+#pragma unroll
+                            for (int q = 0; q < kQ; ++q) {
+                                const float4 xa = tc::lds_v4(tab + (uint32_t)(k0 + 8 * q) * 4u), xb = tc::lds_v4(tab + (uint32_t)(k0 + 8 * q + 4) * 4u);
+                                const float x[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+                                uint32_t p1[4], p2[4];
+#if HELIO_BWD_PACKED2
+                                const tc::f32x2 nc2 = tc::pack2(-ctr, -ctr), k22 = tc::pack2(nk2, nk2), la2 = tc::pack2(la, la);
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const tc::f32x2 d2 = tc::add2(tc::pack2(x[2 * e], x[2 * e + 1]), nc2);
+                                    float a0, a1;
+                                    tc::unpack2(tc::fma2(tc::mul2(d2, k22), d2, la2), a0, a1);
+                                    tc::split_f16x2_packed(tc::pack2(ex2(a0), ex2(a1)).r, p1[e], p2[e]);
+                                }
+#else
+                                float v[8];
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) {
+                                    const float d = x[e] - ctr;
+                                    v[e] = ex2(fmaf(d * nk2, d, la));
+                                }
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) tc::split_f16x2(v[2 * e], v[2 * e + 1], p1[e], p2[e]);
+#endif
+                                const uint32_t off = tc::sw128_offset((uint32_t)r, (uint32_t)(q0 + q));
+                                tc::sts_v4_b32(hi_base + off, p1[0], p1[1], p1[2], p1[3]);
+                                tc::sts_v4_b32(lo_base + off, p2[0], p2[1], p2[2], p2[3]);
+                            }
+                        } else {
 #pragma unroll
                         for (int q = 0; q < kQ; ++q) {
                             const float4 xs = tc::lds_v4(tab + (uint32_t)(k0 + 4 * q) * 4u);
@@ -941,6 +1029,7 @@ splat_bwd_tc_kernel(const float4* __restrict__ params, const int* __restrict__ c
                             const uint32_t off = tc::sw128_offset((uint32_t)r, (uint32_t)(q0 + q));
                             tc::sts_v4(hi_base + off, hi[0], hi[1], hi[2], hi[3]);
                             tc::sts_v4(lo_base + off, lo[0], lo[1], lo[2], lo[3]);
+                        }
                         }
                         {
                             TC_STAT_BEGIN;
@@ -958,8 +1047,11 @@ splat_bwd_tc_kernel(const float4* __restrict__ params, const int* __restrict__ c
         TC_STAT_FLUSH;
     } else if (warp < C::kMmaWarp) {
         // ================= gradient tile stagers =================
-        const int t = threadIdx.x - C::kAWarps * 32;     // 0..kBRows-1: operand row inside this CTA's share
-        const int gw = t >> 5;
+        // kBAlt groups of kBRows / 32 warps; group sg fills the stages with it % kBAlt == sg
+        const int sw_ = (int)(threadIdx.x >> 5) - C::kAWarps;              // stager warp index
+        const int sg = sw_ / (C::kBRows / 32);                             // group
+        const int gw = sw_ % (C::kBRows / 32);                             // 32-row slab inside the group
+        const int t = gw * 32 + lane;                    // 0..kBRows-1: operand row inside this CTA's share
         const int row_base = (int)cx.rank * C::kBRows;   // first accumulator column this CTA stages
         uint32_t it = 0;
         TC_STAT_DECL;
@@ -970,72 +1062,141 @@ splat_bwd_tc_kernel(const float4* __restrict__ params, const int* __restrict__ c
             if (tile_empty(tile)) continue;
             const int b = tile / nblocks;
             const float* gb = g_img + (size_t)b * R * R;
+            float gs = 1.f;                                  // f16x3: per-image power-of-two scale of the gradient operand
+            if constexpr (PREC == 1) gs = pow2i(grad_scale_exponent(__ldg(gmax + b)));
 #pragma unroll 1
             for (int prod = 0; prod < 2; ++prod) {
 #pragma unroll 1
                 for (int pbk = 0; pbk < pblocks; ++pbk) {
 #pragma unroll 1
                     for (int c = 0; c < kchunks; ++c, ++it) {
+                        if (C::kBAlt > 1 && (int)(it % C::kBAlt) != sg) continue;  // another group's turn (the loop still counts the stage)
                         const int s = it % C::kStages;
                         const int k0 = c * C::kKC;
                         float4 vals[8];
-                        uint32_t offs[8];
-                        // whole operand tile inside the image: no per-element bounds checks (the common case)
-                        const bool inside = vec && k0 + C::kKC <= R && pbk * NT + row_base + C::kBRows <= R;
-                        if (prod == 0) {
-                            // operand row = image row i (accumulator column), K = image column j:
-                            // 8 lanes cover one 128-byte row segment, a warp instruction covers 4 rows
-                            const int row0 = gw * 32 + (lane >> 3), ch = lane & 7;
-                            if (inside) {
-                                const float4* src = reinterpret_cast<const float4*>(gb + (size_t)(pbk * NT + row_base + row0) * R + k0) + ch;
+                        const int row0 = gw * 32 + (lane >> 3), ch = lane & 7;     // product 0: 8 lanes per 128-byte row segment
+                        const int j = pbk * NT + row_base + t;                     // product 1: this thread's image column
+                        // 32 K values (kb .. kb + 31) of this thread's share of the operand tile -> vals[8]
+                        //   product 0: operand row = image row i (accumulator column), K = image column j: 8 lanes cover one
+                        //              128-byte row segment, a warp instruction covers 4 rows; vals[q] = row (row0 + 4 q), K kb + 4 ch .. + 3
+                        //   product 1: operand row = image column j, K = image row i: lanes read consecutive columns of one
+                        //              image row (coalesced), transposing in registers; vals[q] = K kb + 4 q .. + 3 of row t
+                        auto load32 = [&](const int kb) {
+                            // whole operand tile inside the image: no per-element bounds checks (the common case)
+                            const bool inside = vec && kb + 32 <= R && pbk * NT + row_base + C::kBRows <= R;
+                            if (prod == 0) {
+                                if (inside) {
+                                    const float4* src = reinterpret_cast<const float4*>(gb + (size_t)(pbk * NT + row_base + row0) * R + kb) + ch;
 #pragma unroll
-                                for (int q = 0; q < 8; ++q) vals[q] = __ldg(src + (size_t)q * R);   // 4 rows = R float4
-                            } else {
+                                    for (int q = 0; q < 8; ++q) vals[q] = __ldg(src + (size_t)q * R);   // 4 rows = R float4
+                                } else {
 #pragma unroll
-                                for (int q = 0; q < 8; ++q) {
-                                    const int i = pbk * NT + row_base + row0 + q * 4, j = k0 + ch * 4;
-                                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                                    if (i < R) {
-                                        const float* src = gb + (size_t)i * R + j;
-                                        if (vec && j + 3 < R) {
-                                            v = __ldg(reinterpret_cast<const float4*>(src));
-                                        } else {
-                                            if (j < R) v.x = __ldg(src);
-                                            if (j + 1 < R) v.y = __ldg(src + 1);
-                                            if (j + 2 < R) v.z = __ldg(src + 2);
-                                            if (j + 3 < R) v.w = __ldg(src + 3);
+                                    for (int q = 0; q < 8; ++q) {
+                                        const int i = pbk * NT + row_base + row0 + q * 4, jj = kb + ch * 4;
+                                        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                                        if (i < R) {
+                                            const float* src = gb + (size_t)i * R + jj;
+                                            if (vec && jj + 3 < R) {
+                                                v = __ldg(reinterpret_cast<const float4*>(src));
+                                            } else {
+                                                if (jj < R) v.x = __ldg(src);
+                                                if (jj + 1 < R) v.y = __ldg(src + 1);
+                                                if (jj + 2 < R) v.z = __ldg(src + 2);
+                                                if (jj + 3 < R) v.w = __ldg(src + 3);
+                                            }
                                         }
+                                        vals[q] = v;
                                     }
-                                    vals[q] = v;
+                                }
+                            } else {
+                                if (inside) {
+                                    const float* src = gb + (size_t)kb * R + j;
+#pragma unroll
+                                    for (int q = 0; q < 8; ++q) {
+                                        vals[q].x = __ldg(src + (size_t)(4 * q) * R);
+                                        vals[q].y = __ldg(src + (size_t)(4 * q + 1) * R);
+                                        vals[q].z = __ldg(src + (size_t)(4 * q + 2) * R);
+                                        vals[q].w = __ldg(src + (size_t)(4 * q + 3) * R);
+                                    }
+                                } else {
+#pragma unroll
+                                    for (int q = 0; q < 8; ++q) {
+                                        float x[4];
+#pragma unroll
+                                        for (int e = 0; e < 4; ++e) {
+                                            const int i = kb + 4 * q + e;
+                                            x[e] = (i < R && j < R) ? __ldg(gb + (size_t)i * R + j) : 0.f;
+                                        }
+                                        vals[q] = make_float4(x[0], x[1], x[2], x[3]);
+                                    }
                                 }
                             }
+                        };
+                        const uint32_t hi_base = cx.smem_u + (uint32_t)(s * C::kStageBytes + 2 * C::kABytes);
+                        const uint32_t lo_base = hi_base + C::kBBytes;
+                        if constexpr (PREC == 1) {
+                            // two halves of 32 K values; rows of the fp16 tiles hold 64 K values (128 bytes) per piece
+#pragma unroll 1
+                            for (int h = 0; h < 2; ++h) {
+                                load32(k0 + 32 * h);
+                                if (h == 0) {
+                                    TC_STAT_BEGIN;
+                                    cx.producer_acquire(s, (it / C::kStages) & 1);
+                                    TC_STAT_END(2);
+                                }
+                                if (prod == 0) {
+                                    // this lane's 4 K values = bytes 64 h + 8 ch .. + 7 of the row: half of 16-byte chunk 4 h + ch / 2
+#pragma unroll
+                                    for (int q = 0; q < 8; ++q) {
+                                        uint32_t p1a, p2a, p1b, p2b;
+#if HELIO_BWD_PACKED2
+                                        const tc::f32x2 gs2 = tc::pack2(gs, gs);
+                                        tc::split_f16x2_packed(tc::mul2(tc::pack2(vals[q].x, vals[q].y), gs2).r, p1a, p2a);
+                                        tc::split_f16x2_packed(tc::mul2(tc::pack2(vals[q].z, vals[q].w), gs2).r, p1b, p2b);
+#else
+                                        tc::split_f16x2(vals[q].x * gs, vals[q].y * gs, p1a, p2a);
+                                        tc::split_f16x2(vals[q].z * gs, vals[q].w * gs, p1b, p2b);
+#endif
+                                        const uint32_t row = (uint32_t)(row0 + q * 4), sw = row & 7u;
+                                        const uint32_t off = (row >> 3) * 1024u + sw * 128u + ((((uint32_t)(4 * h) + ((uint32_t)ch >> 1)) ^ sw) << 4) + 8u * ((uint32_t)ch & 1u);
+                                        tc::sts_v2_b32(hi_base + off, p1a, p1b);
+                                        tc::sts_v2_b32(lo_base + off, p2a, p2b);
+                                    }
+                                } else {
+                                    // vals[2 m], vals[2 m + 1] = K values 32 h + 8 m .. + 7 of row t: 16-byte chunk 4 h + m
+#pragma unroll
+                                    for (int m = 0; m < 4; ++m) {
+                                        uint32_t p1[4], p2[4];
+#if HELIO_BWD_PACKED2
+                                        const tc::f32x2 gs2 = tc::pack2(gs, gs);
+                                        tc::split_f16x2_packed(tc::mul2(tc::pack2(vals[2 * m].x, vals[2 * m].y), gs2).r, p1[0], p2[0]);
+                                        tc::split_f16x2_packed(tc::mul2(tc::pack2(vals[2 * m].z, vals[2 * m].w), gs2).r, p1[1], p2[1]);
+                                        tc::split_f16x2_packed(tc::mul2(tc::pack2(vals[2 * m + 1].x, vals[2 * m + 1].y), gs2).r, p1[2], p2[2]);
+                                        tc::split_f16x2_packed(tc::mul2(tc::pack2(vals[2 * m + 1].z, vals[2 * m + 1].w), gs2).r, p1[3], p2[3]);
+#else
+                                        tc::split_f16x2(vals[2 * m].x * gs, vals[2 * m].y * gs, p1[0], p2[0]);
+                                        tc::split_f16x2(vals[2 * m].z * gs, vals[2 * m].w * gs, p1[1], p2[1]);
+                                        tc::split_f16x2(vals[2 * m + 1].x * gs, vals[2 * m + 1].y * gs, p1[2], p2[2]);
+                                        tc::split_f16x2(vals[2 * m + 1].z * gs, vals[2 * m + 1].w * gs, p1[3], p2[3]);
+#endif
+                                        const uint32_t off = tc::sw128_offset((uint32_t)t, (uint32_t)(4 * h + m));
+                                        tc::sts_v4_b32(hi_base + off, p1[0], p1[1], p1[2], p1[3]);
+                                        tc::sts_v4_b32(lo_base + off, p2[0], p2[1], p2[2], p2[3]);
+                                    }
+                                }
+                            }
+                            {
+                                TC_STAT_BEGIN;
+                                cx.producer_commit(s);
+                                TC_STAT_END(1);
+                            }
+                        } else {
+                        load32(k0);
+                        uint32_t offs[8];
+                        if (prod == 0) {
 #pragma unroll
                             for (int q = 0; q < 8; ++q) offs[q] = tc::sw128_offset((uint32_t)(row0 + q * 4), (uint32_t)ch);
                         } else {
-                            // operand row = image column j (accumulator column), K = image row i:
-                            // lanes read consecutive columns of one image row (coalesced), transposing in registers
-                            const int j = pbk * NT + row_base + t;
-                            if (inside) {
-                                const float* src = gb + (size_t)k0 * R + j;
-#pragma unroll
-                                for (int q = 0; q < 8; ++q) {
-                                    vals[q].x = __ldg(src + (size_t)(4 * q) * R);
-                                    vals[q].y = __ldg(src + (size_t)(4 * q + 1) * R);
-                                    vals[q].z = __ldg(src + (size_t)(4 * q + 2) * R);
-                                    vals[q].w = __ldg(src + (size_t)(4 * q + 3) * R);
-                                }
-                            } else {
-#pragma unroll
-                                for (int q = 0; q < 8; ++q) {
-                                    float x[4];
-#pragma unroll
-                                    for (int e = 0; e < 4; ++e) {
-                                        const int i = k0 + 4 * q + e;
-                                        x[e] = (i < R && j < R) ? __ldg(gb + (size_t)i * R + j) : 0.f;
-                                    }
-                                    vals[q] = make_float4(x[0], x[1], x[2], x[3]);
-                                }
-                            }
 #pragma unroll
                             for (int q = 0; q < 8; ++q) offs[q] = tc::sw128_offset((uint32_t)t, (uint32_t)q);
                         }
@@ -1047,8 +1208,6 @@ splat_bwd_tc_kernel(const float4* __restrict__ params, const int* __restrict__ c
                             cx.producer_acquire(s, (it / C::kStages) & 1);
                             TC_STAT_END(2);
                         }
-                        const uint32_t hi_base = cx.smem_u + (uint32_t)(s * C::kStageBytes + 2 * C::kABytes);
-                        const uint32_t lo_base = hi_base + C::kBBytes;
 #pragma unroll
                         for (int q = 0; q < 8; ++q) {
                             float4 h, l;
@@ -1068,6 +1227,7 @@ splat_bwd_tc_kernel(const float4* __restrict__ params, const int* __restrict__ c
                             TC_STAT_END(1);
                         }
 #endif
+                        }
                     }
                 }
             }
@@ -1108,8 +1268,12 @@ splat_bwd_tc_kernel(const float4* __restrict__ params, const int* __restrict__ c
         }
     } else {
         // ================= epilogue: accumulator -> moments =================
+        // kEpiSplit warps share a TMEM lane quarter, each folding 1 / kEpiSplit of an accumulator's columns; their partial
+        // moments are combined through shared memory at the end of the tile (slot by tile parity, one named barrier)
         const int q = warp & 3;
-        uint32_t sub = 0;
+        const int eh = (warp - C::kEpiWarp0) >> 2;            // which share of the columns
+        constexpr int kColsPer = NT / C::kEpiSplit;
+        uint32_t sub = 0, tdone = 0;
         auto tile_params = [&](int tile, bool& live) {
             const int b = tile / nblocks, nb = tile % nblocks;
             const int n = nb * kTileH + (int)cx.rank * C::kM + q * 32 + lane;
@@ -1133,6 +1297,10 @@ splat_bwd_tc_kernel(const float4* __restrict__ params, const int* __restrict__ c
                 const float ctr = prod == 0 ? p.x : p.y;
                 const uint32_t tab = prod == 0 ? cx.sX_u : cx.sY_u;
                 float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+#if HELIO_BWD_PACKED2
+                tc::f32x2 s0p = tc::pack2(0.f, 0.f), s1p = s0p, s2p = s0p;      // even / odd columns
+                const tc::f32x2 nc2 = tc::pack2(-ctr, -ctr), k22 = tc::pack2(nk2, nk2);
+#endif
 #pragma unroll 1
                 for (int pbk = 0; pbk < pblocks; ++pbk, ++sub) {
                     const int acc = sub & 1;
@@ -1145,7 +1313,7 @@ splat_bwd_tc_kernel(const float4* __restrict__ params, const int* __restrict__ c
                     const uint32_t taddr = cx.tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * NT);
                     const int col0 = pbk * NT;
 #pragma unroll 1
-                    for (int cb = 0; cb < NT; cb += 32) {
+                    for (int cb = eh * kColsPer; cb < (eh + 1) * kColsPer; cb += 32) {
                         if (col0 + cb >= R) break;
                         float v[32];
                         tc::tmem_ld_32x32(taddr + cb, v);
@@ -1153,6 +1321,20 @@ splat_bwd_tc_kernel(const float4* __restrict__ params, const int* __restrict__ c
                         for (int e4 = 0; e4 < 32; e4 += 4) {
                             const float4 xs = tc::lds_v4(tab + (uint32_t)(col0 + cb + e4) * 4u);
                             const float x[4] = {xs.x, xs.y, xs.z, xs.w};
+#if HELIO_BWD_PACKED2
+#pragma unroll
+                            for (int e = 0; e < 4; e += 2) {
+                                // columns >= R hold exact zeros (their operand rows are zero)
+                                const tc::f32x2 d2 = tc::add2(tc::pack2(x[e], x[e + 1]), nc2);
+                                const tc::f32x2 dd2 = tc::mul2(d2, d2);
+                                float a0, a1;
+                                tc::unpack2(tc::mul2(dd2, k22), a0, a1);
+                                const tc::f32x2 w2 = tc::mul2(tc::pack2(ex2(a0), ex2(a1)), tc::pack2(v[e4 + e], v[e4 + e + 1]));
+                                s0p = tc::add2(s0p, w2);
+                                s1p = tc::fma2(w2, d2, s1p);
+                                s2p = tc::fma2(w2, dd2, s2p);
+                            }
+#else
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
                                 // columns >= R hold exact zeros (their operand rows are zero)
@@ -1163,15 +1345,38 @@ splat_bwd_tc_kernel(const float4* __restrict__ params, const int* __restrict__ c
                                 s1 = fmaf(w, d, s1);
                                 s2 = fmaf(w, dd, s2);
                             }
+#endif
                         }
                     }
                     cx.epilogue_release(acc);
                 }
+#if HELIO_BWD_PACKED2
+                {
+                    float lo, hi;
+                    tc::unpack2(s0p, lo, hi), s0 = lo + hi;
+                    tc::unpack2(s1p, lo, hi), s1 = lo + hi;
+                    tc::unpack2(s2p, lo, hi), s2 = lo + hi;
+                }
+#endif
                 if (prod == 0) {
                     S0 = s0 * p.w, Sx = s1 * p.w, S2 = s2 * p.w;
                 } else {
                     Sy = s1, S2 += s2;
                 }
+            }
+            if constexpr (C::kEpiSplit > 1) {
+                static_assert(C::kEpiSplit == 2, "two-way split");
+                const uint32_t slot = cx.epi_u + (uint32_t)((tdone & 1u) * 2048u + (uint32_t)(q * 32 + lane) * 16u);
+                if (eh == 1) tc::sts_v4(slot, S0, Sx, Sy, S2);
+                asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");      // the two warps of this lane quarter
+                ++tdone;
+                if (eh == 1) continue;                        // the first warp of the quarter owns the result
+                const float4 o = tc::lds_v4_volatile(slot);
+                S0 += o.x, Sx += o.y, Sy += o.z, S2 += o.w;
+            }
+            if constexpr (PREC == 1) {                       // undo 2^14 (Gaussian operand) x 2^sexp (gradient operand): exact
+                const float us = pow2i(-14 - grad_scale_exponent(__ldg(gmax + b)));
+                S0 *= us, Sx *= us, Sy *= us, S2 *= us;
             }
             if (live) moments[(size_t)b * N + (index ? __ldg(index + (size_t)b * N + n) : n)] = make_float4(S0, Sx, Sy, S2);
         }
@@ -1183,24 +1388,35 @@ splat_bwd_tc_kernel(const float4* __restrict__ params, const int* __restrict__ c
 inline bool splat_tc_bwd_supported(int B, int N, int R) { return B > 0 && N > 0 && R >= 8 && R <= kTcMaxR; }
 inline bool splat_tc_bwd_preferred(int B, int N, int R) { return R >= 48; }
 
-template <int NT, int CG>
-inline cudaError_t launch_splat_bwd_tc(const float* params, const int* counts, const int* index, const float* g_img, float* moments,
-                                       int B, int N, int R, float width, float height, int num_sms, cudaStream_t st) {
-    using C = SplatBwdTc<NT, CG>;
+template <int NT, int CG, int PREC = 0>
+inline cudaError_t launch_splat_bwd_tc(const float* params, const int* counts, const int* index, const float* g_img, const float* gmax,
+                                       float* moments, int B, int N, int R, float width, float height, int num_sms, cudaStream_t st) {
+    using C = SplatBwdTc<NT, CG, PREC>;
     const int nblocks = (N + C::kM * CG - 1) / (C::kM * CG);
     const long long num_tiles = (long long)B * nblocks;
     if (num_tiles > 0x7fffffffLL) return cudaErrorInvalidValue;
-    return launch_tc_groups<CG>(splat_bwd_tc_kernel<NT, CG>, num_tiles, num_sms, C::kThreads, C::kSmemBytes, st,
-                                reinterpret_cast<const float4*>(params), counts, index, g_img, reinterpret_cast<float4*>(moments),
+    return launch_tc_groups<CG>(splat_bwd_tc_kernel<NT, CG, PREC>, num_tiles, num_sms, C::kThreads, C::kSmemBytes, st,
+                                reinterpret_cast<const float4*>(params), counts, index, g_img, gmax, reinterpret_cast<float4*>(moments),
                                 N, R, make_axis(width, R), make_axis(height, R), nblocks, (int)num_tiles);
 }
 
 // counts / index (may be NULL): culled (compacted) parameter rows and their original heliostat indices (cull.cuh); the
 // caller zero-fills `moments` first, only the kept heliostats are written
+// gmax (may be NULL = 3xTF32): per-image max |g_img[b]|; when given, the f16x3 operand format (K = 64 per stage) is used
 inline cudaError_t splat_tc_bwd(const float* params, const float* g_img, float* moments, int B, int N, int R, float width,
                                 float height, int num_sms, cudaStream_t st, int pair = 0, const int* counts = nullptr,
-                                const int* index = nullptr) {
-#define HELIO_BWD(NT_, CG_) launch_splat_bwd_tc<NT_, CG_>(params, counts, index, g_img, moments, B, N, R, width, height, num_sms, st)
+                                const int* index = nullptr, const float* gmax = nullptr) {
+    if (gmax != nullptr) {
+#define HELIO_BWD16(NT_, CG_) launch_splat_bwd_tc<NT_, CG_, 1>(params, counts, index, g_img, gmax, moments, B, N, R, width, height, num_sms, st)
+        if (R > 128) {
+            if (pair != 1 && num_sms >= 2 && (pair == 2 || N > 128)) return HELIO_BWD16(256, 2);
+            return HELIO_BWD16(256, 1);
+        }
+        if (R > 64) return HELIO_BWD16(128, 1);
+        return HELIO_BWD16(64, 1);
+#undef HELIO_BWD16
+    }
+#define HELIO_BWD(NT_, CG_) launch_splat_bwd_tc<NT_, CG_>(params, counts, index, g_img, nullptr, moments, B, N, R, width, height, num_sms, st)
     if (R > 128) {
         // CTA pairs need a second block of 128 heliostats to be worth it
         if (pair != 1 && num_sms >= 2 && (pair == 2 || N > 128)) return HELIO_BWD(256, 2);

@@ -37,9 +37,32 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// try_wait with a suspend-time hint: the hardware parks the thread until the phase completes (or the hint, in nanoseconds,
+// runs out) instead of returning after its short default limit.  Without it the waiting warps of the pipeline spin --
+// ncu counted ~1e9 of the 3.5e9 warp instructions of the backward splat in TRYWAIT / BRA loops -- and steal issue slots
+// from the warps that share their scheduler (21 warps per SM: the kernel is bound by instruction issue).
+#ifndef HELIO_MBAR_SUSPEND_NS
+#define HELIO_MBAR_SUSPEND_NS 20000
+#endif
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"((uint32_t)HELIO_MBAR_SUSPEND_NS)
+        : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+#if HELIO_MBAR_SUSPEND_NS > 0
+    while (!mbar_try_wait_hint(bar, parity)) {
+    }
+#else
     while (!mbar_try_wait(bar, parity)) {
     }
+#endif
 }
 
 // generic-proxy smem writes -> visible to the async proxy (tcgen05.mma operand reads)
@@ -229,6 +252,11 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
 __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
     return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+__device__ __forceinline__ void sts_v4_b32(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+// v (already scaled into fp16 range) -> two fp16 pieces, p1 = rn(v), p2 = rn(v - p1): 11 + 11 significant bits
+__device__ __forceinline__ void split_f16x2(float v0, float v1, uint32_t& p1, uint32_t& p2);
 __device__ __forceinline__ void sts_v2_b32(uint32_t addr, uint32_t a, uint32_t b) {
     asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
 }
@@ -241,6 +269,15 @@ __device__ __forceinline__ uint32_t f2h2(float lo, float hi) {
 __device__ __forceinline__ void h22f(uint32_t h, float& lo, float& hi) {
     asm("{\n\t.reg .f16 a, b;\n\tmov.b32 {a, b}, %2;\n\tcvt.f32.f16 %0, a;\n\tcvt.f32.f16 %1, b;\n\t}" : "=f"(lo), "=f"(hi) : "r"(h));
 }
+
+__device__ __forceinline__ void split_f16x2(float v0, float v1, uint32_t& p1, uint32_t& p2) {
+    p1 = f2h2(v0, v1);
+    float f0, f1;
+    h22f(p1, f0, f1);
+    p2 = f2h2(v0 - f0, v1 - f1);
+}
+struct f32x2;
+__device__ __forceinline__ void split_f16x2_packed(unsigned long long v2, uint32_t& p1, uint32_t& p2);
 
 // split an fp32 into a tf32-exact high part and the fp32 remainder (the tensor core reads the top
 // 19 bits of each operand; hi + lo == v exactly)
@@ -282,6 +319,21 @@ __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
     f32x2 d;
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d.r) : "l"(a.r), "l"(b.r), "l"(c.r));
     return d;
+}
+
+// Truncating split of a pair {v0, v1} (already scaled into fp16 range) into fp16 pieces: hi = v with the 13 low mantissa
+// bits cleared (exactly an fp16 value once |v| >= 2^-14), lo = v - hi (exact), p1 = cvt(hi), p2 = rn(lo).  The same
+// 11 + 11 bits as the rounding split to within one unit of the last place (|v - p1 - p2| <= 2^-21 |v|, what the tf32
+// hi / lo split keeps), with two logic operations and one packed subtraction instead of two fp16 -> fp32 conversions.
+// Below 2^-14 the first conversion rounds to a subnormal: absolute error <= 2^-25, i.e. 2^-39 of the 2^14 scale.
+__device__ __forceinline__ void split_f16x2_packed(unsigned long long v2, uint32_t& p1, uint32_t& p2) {
+    float v0, v1, r0, r1;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(v0), "=f"(v1) : "l"(v2));
+    const float h0 = __uint_as_float(__float_as_uint(v0) & 0xFFFFE000u), h1 = __uint_as_float(__float_as_uint(v1) & 0xFFFFE000u);
+    p1 = f2h2(h0, h1);
+    f32x2 d = add2(f32x2{v2}, pack2(-h0, -h1));
+    unpack2(d, r0, r1);
+    p2 = f2h2(r0, r1);
 }
 
 }  // namespace tc

@@ -74,10 +74,19 @@ HELIO_API int helio_set_tc_pair_mode(int mode);
 /* Forward splat operand format on the tcgen05 path.  0: 3xTF32 everywhere.  1: "f16x3" everywhere -- both operands of
  * the forward are Gaussians in [0,1]; they are scaled by 2^14 and split into two fp16 pieces (11 + 11 significant bits,
  * the accuracy the tf32 hi/lo split keeps), three kind::f16 MMAs per K-step, fp32 accumulation, exact 2^-28 unscale in
- * the epilogue.  2 (default): auto = f16x3 for images up to 128 pixels a side (operand-generation-bound shapes, where
- * its half-size stages and cheaper MMAs pay), 3xTF32 above (the contraction BASELINE.json names for the headline shape).
+ * the epilogue.  2 (default): auto = f16x3 (same measured accuracy as 3xTF32, half the tensor work: faster at every
+ * shape); mode 0 keeps the 3xTF32 contraction BASELINE.json names selectable.
  * Process-wide; initial value from HELIO_FWD_PREC.  The backward (unbounded image gradient) always uses 3xTF32. */
 HELIO_API int helio_set_fwd_precision(int mode);
+
+/* Backward splat operand format inside helio_step_bwd.  0: 3xTF32.  1: "f16x3, K = 64" -- the Gaussian operand scaled by
+ * 2^14 as in the forward, the image gradient scaled PER IMAGE by the power of two that brings max |dL/dimg[b]| under 2^14
+ * (the loss backward produces that maximum on the way), both split into two fp16 pieces; a 64 KB pipeline stage then
+ * covers 64 instead of 32 steps of the contraction with the same twelve MMAs (kind::f16): half the tensor work, half the
+ * stage hand-overs.  Accuracy as 3xTF32 (22 significant bits per operand; entries more than 2^17 below their image's
+ * maximum keep an absolute error below 2^-38 of that maximum).  helio_splat_bwd (arbitrary g_img, no scratch for the
+ * maxima) always uses 3xTF32.  Process-wide; initial value from HELIO_BWD_PREC. */
+HELIO_API int helio_set_bwd_precision(int mode);
 
 /* Opt-in per-kernel timing (no reference counterpart; SURVEY.md section 5 "tracing / profiling").
  * helio_profile_enable(1) clears earlier records and makes every entry point record a CUDA event pair

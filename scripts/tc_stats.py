@@ -19,6 +19,7 @@ from doodle_b200 import _lib
 ap = argparse.ArgumentParser()
 ap.add_argument("--B", type=int, default=4096); ap.add_argument("--N", type=int, default=2000); ap.add_argument("--R", type=int, default=256)
 ap.add_argument("--what", default="both"); ap.add_argument("--prec", type=int, default=0); ap.add_argument("--pair", type=int, default=0)
+ap.add_argument("--bprec", type=int, default=0, help="backward operand format: 0 = 3xTF32, 1 = f16x3 K=64 (debug entry)")
 a = ap.parse_args()
 lib = _lib.load()
 assert hasattr(lib, "helio_debug_tc_stats"), "load a -DHELIO_TC_STATS=1 build through HELIO_LIB_PATH"
@@ -35,23 +36,31 @@ P = lambda t: C.c_void_p(t.data_ptr())
 lib.helio_set_fwd_precision(a.prec); lib.helio_set_tc_pair_mode(a.pair)
 
 
+gmax = g.abs().amax((1, 2)).contiguous()
+
+
 def run(what):
-    f = (lambda: lib.helio_splat_fwd(P(p), B, N, R, 15.0, 15.0, P(img), 2, None)) if what == "fwd" else \
-        (lambda: lib.helio_splat_bwd(P(p), P(g), B, N, R, 15.0, 15.0, P(mom), 2, None))
+    if what == "fwd":
+        f = lambda: lib.helio_splat_fwd(P(p), B, N, R, 15.0, 15.0, P(img), 2, None)
+    elif a.bprec == 1:
+        lib.helio_debug_splat_bwd_f16.argtypes = [C.c_void_p] * 3 + [C.c_int] * 3 + [C.c_float] * 2 + [C.c_void_p] * 2
+        f = lambda: lib.helio_debug_splat_bwd_f16(P(p), P(g), P(gmax), B, N, R, 15.0, 15.0, P(mom), None)
+    else:
+        f = lambda: lib.helio_splat_bwd(P(p), P(g), B, N, R, 15.0, 15.0, P(mom), 2, None)
     for _ in range(2):
         assert f() == 0, lib.helio_last_error()
     torch.cuda.synchronize()
     lib.helio_debug_tc_stats(None, 1)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); f(); e1.record(); torch.cuda.synchronize()
-    st = np.zeros((160, 16, 4), np.uint64)
+    st = np.zeros((160, 24, 4), np.uint64)
     lib.helio_debug_tc_stats(st.ctypes.data, 0)
     st = st.astype(np.float64)
     used = st[:, :, 0].sum(1) > 0
     ncta = int(used.sum())
-    print(f"== {what}: B={B} N={N} R={R} prec={a.prec}: {e0.elapsed_time(e1):.3f} ms, {ncta} CTAs reporting")
+    print(f"== {what}: B={B} N={N} R={R} prec={a.prec} bprec={a.bprec}: {e0.elapsed_time(e1):.3f} ms, {ncta} CTAs reporting")
     tot = st[used]
-    warps = [w for w in range(16) if tot[:, w, 0].max() > 0]
+    warps = [w for w in range(24) if tot[:, w, 0].max() > 0]
     kernel_cycles = tot[:, :, 0].max()
     print(f"   longest role loop: {kernel_cycles/1e6:.3f} Mcycles")
     for w in warps:
