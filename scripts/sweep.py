@@ -37,7 +37,7 @@ def main():
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    tensor_peak = float(peaks.get("bf16_tflops_sustained") or 1400.0) / 6.0     # TF32 / 3 (3xTF32), TFLOP/s
+    tensor_peak = float(peaks.get("bf16_tflops_sustained") or 1400.0) / 3.0     # f16x3 (both splats by default): three fp16 MMAs per product, TFLOP/s
     hbm_peak = float(peaks.get("hbm_gbs") or 6500.0)
     cpu_cache = {}
     for (N, R, B) in grid:
@@ -93,7 +93,7 @@ def main():
         line = dict(N=N, R=R, B_per_gpu=B, n_gpus=world, splat=args.splat, ms_per_step=round(ms, 4), env_steps_per_s=round(1e3 / ms, 2),
                     evals_per_s=evals / (ms * 1e-3), roofline_ms=dict(tensor=round(t_tensor, 4), hbm=round(t_hbm, 4)),
                     frac_of_roofline=round(max(t_tensor, t_hbm) / ms, 4), bound="tensor" if t_tensor > t_hbm else "hbm",
-                    graph_replay=replayed, kernels_us=k, setup_s=round(setup_s, 3), mem_gb=round(torch.cuda.max_memory_allocated() / 1e9, 2))
+                    tensor_model="f16x3: bf16_sustained/3", graph_replay=replayed, kernels_us=k, setup_s=round(setup_s, 3), mem_gb=round(torch.cuda.max_memory_allocated() / 1e9, 2))
         if args.cpu and rank == 0:
             if (N, R) not in cpu_cache:
                 f = bench.cpu_step_factory(N, R, 1, os.cpu_count() or 1)
