@@ -29,6 +29,7 @@
 // Accuracy: hi*hi + hi*lo + lo*hi with fp32 accumulation drops only lo*lo (~2^-22 relative) and
 // the truncation of lo (~2^-21): fp32-class results from the tensor pipe.
 #pragma once
+#include <type_traits>
 #include "helio_common.cuh"
 #include "tc_common.cuh"
 
@@ -37,6 +38,27 @@
 #endif
 #ifndef HELIO_PACKED2
 #define HELIO_PACKED2 0
+#endif
+#ifndef HELIO_FWD_F16_TRUNC
+// f16x3 forward producers: 1 = packed fp32x2 exponent arithmetic + truncating two-piece split (piece 1 = the top 11
+// significand bits, piece 2 = fp16(v - piece 1): |error| <= 2^-22 v, the K3 split), 0 = round-to-nearest piece 1 with the
+// residual taken through an fp16 -> fp32 round trip (2^-23 v, 1.5 more instructions per Gaussian).
+#define HELIO_FWD_F16_TRUNC 1
+#endif
+#ifndef HELIO_FWD_SWP
+#define HELIO_FWD_SWP 1     // f16x3 forward producers software-pipelined across stages (see the kernel)
+#endif
+#ifndef HELIO_FWD_SWP_MIN_N
+// the pipeline restarts at every tile (its first stage is evaluated on its own), so it needs several stages per sun to pay:
+// measured on B200 -3.5 % at N = 2000 (R = 256), -9 % at N = 5000 (R = 64), +10 % at N = 50 (two stages per tile)
+#define HELIO_FWD_SWP_MIN_N 256
+#endif
+#ifndef HELIO_FWD_FULL_STAGE
+// 1: stages whose 32 heliostats all exist (every stage but a sun's last) skip the per-heliostat bounds work: no index clamps
+// on the parameter loads (one pointer, four immediate offsets) and no validity selects on the exponent offsets.  Measured on
+// B200: -7 % with the round-to-nearest split, nothing on top of the truncating split (the producers are then no longer bound by
+// instruction issue) at +40 % code size, so it stays an A/B switch.
+#define HELIO_FWD_FULL_STAGE 0
 #endif
 #ifndef HELIO_BWD_DEFER
 #define HELIO_BWD_DEFER 0
@@ -51,6 +73,26 @@
 #endif
 #ifndef HELIO_RELAXED_ARRIVE
 #define HELIO_RELAXED_ARRIVE 0   // 1: producers signal "stage written" with mbarrier.arrive.relaxed (see tc_common.cuh)
+#endif
+#ifndef HELIO_CONSUMER_FENCE
+// Where the generic -> async proxy fence between the producers' st.shared and the tensor core's operand reads sits.
+// 0: in every producer thread before its warp's arrive (the CUTLASS pattern).  fence.proxy.async compiles to MEMBAR.ALL.CTA +
+//    FENCE.VIEW.ASYNC.S, and the MEMBAR also waits for the thread's outstanding global loads (the parameter prefetch).
+// 1: in the MMA warp after its wait on the full barrier: st.shared -> __syncwarp -> arrive.release -> wait.acquire ->
+//    fence.proxy.async -> tcgen05.mma is a causality chain with the proxy fence in it (PTX memory model, proxy-preserved base
+//    causality order), and the producers no longer stall on a membar.
+#define HELIO_CONSUMER_FENCE 0
+#endif
+#ifndef HELIO_BWD_STAGER_ROWMAP
+#define HELIO_BWD_STAGER_ROWMAP 0
+#endif
+#ifndef HELIO_EPI_SLEEP_FWD_NS
+// nanosleep between the epilogue warps' polls of the accumulator-full barrier.  The polls are 12-16 % of the warp instructions
+// the two kernels execute (ncu source page); 256 / 1000 / 4000 ns instead of 64 changed neither kernel's time on B200.
+#define HELIO_EPI_SLEEP_FWD_NS 64
+#endif
+#ifndef HELIO_EPI_SLEEP_BWD_NS
+#define HELIO_EPI_SLEEP_BWD_NS 64
 #endif
 #ifndef HELIO_TC_STATS
 #define HELIO_TC_STATS 0    // 1: per-warp cycle accounting of the pipeline roles (debug builds only; scripts/tc_stats.py)
@@ -233,7 +275,9 @@ struct SplatTcCtx {
 
     // producer warp: stage s written (all lanes) -> one arrival on the group's full barrier
     __device__ __forceinline__ void producer_commit(int s) const {
+#if !HELIO_CONSUMER_FENCE
         tc::fence_proxy_async_smem();
+#endif
         __syncwarp();
         if ((threadIdx.x & 31) == 0) {
 #if HELIO_RELAXED_ARRIVE
@@ -328,6 +372,9 @@ struct SplatTcCtx {
     }
     __device__ __forceinline__ void mma_wait_full(int s, uint32_t ph) const {
         tc::mbar_wait(&full[s], ph);
+#if HELIO_CONSUMER_FENCE
+        tc::fence_proxy_async_all();
+#endif
         tc::tc_fence_after();
     }
     __device__ __forceinline__ void mma_wait_tempty(int acc, uint32_t aph) const {
@@ -407,19 +454,130 @@ splat_fwd_tc_kernel(const float4* __restrict__ params, const int* __restrict__ c
         constexpr int kRS = 4;                           // rows per step
         constexpr int kSteps = kRows / kRS;
         static_assert(PSX == 1 || PSX == 2, "producer split");
-        const bool isA = warp < C::kAWarps;
+        static_assert(kSteps % 2 == 0, "a pair of steps covers one 8-row swizzle atom");
+        auto produce = [&](auto is_a_tag) {
+        constexpr bool isA = decltype(is_a_tag)::value;                   // the two operands get their own instantiation: no per-stage selects
         const int pw = isA ? warp : warp - C::kAWarps;                   // producer index inside its operand
         const int wrow = pw * kRows;                                     // first operand row of this warp (CTA-local)
         const int rs = lane >> 3, ch = lane & 7;
         const uint32_t region = (isA ? 0u : (uint32_t)C::kBOff) + (uint32_t)(wrow >> 3) * 1024u;
         const uint32_t lo_delta = isA ? C::kABytes : C::kBBytes;
-        // rows visited by this lane: wrow + kRS*step + rs
+        // rows visited by this lane: wrow + lane_row(step).  A step covers rows {0, 1, 4, 5} or {2, 3, 6, 7} of an 8-row swizzle
+        // atom: two rows whose first 64 bytes land in banks 0-15 and two in banks 16-31, so that the f16x3 stores (8 bytes per
+        // lane, one 64-byte half row per piece) touch every bank exactly twice -- consecutive rows {4 st .. 4 st + 3} put all
+        // four half rows on the same 16 banks (ncu: half of the kernel's shared-memory store wavefronts were conflicts).
+        auto lane_row = [&](int st) -> uint32_t {
+            return 8u * (uint32_t)(st >> 1) + 2u * (uint32_t)(st & 1) + (uint32_t)(rs & 1) + 4u * (uint32_t)(rs >> 1);
+        };
         auto row_off = [&](int st) -> uint32_t {
-            const uint32_t row = (uint32_t)(kRS * st + rs);
+            const uint32_t row = lane_row(st);
             return (row >> 3) * 1024u + (row & 7u) * 128u + ((((uint32_t)ch) ^ (row & 7u)) << 4);
         };
         uint32_t it = 0;                             // global stage counter
         TC_STAT_DECL;
+        if (PREC == 1 && HELIO_FWD_SWP && N >= HELIO_FWD_SWP_MIN_N) {
+            // ---- f16x3, software-pipelined across stages --------------------------------------------------------------------
+            // A warp issues in order, and a stage has two phases that use different pipes: the Gaussians (32 MUFU.EX2 per lane, 8
+            // issue cycles each on the XU, little else) and the split + store (LOP3 / F2FP / FADD2 / STS, no MUFU).  Run back to
+            // back they serialise (ncu: no pipe above 40 %, the scheduler idle 59 % of the cycles); here step st of stage c is
+            // split and stored while step st of stage c + 1 is evaluated into the registers it frees, in one basic block, so
+            // the MUFUs of one stage fill under the ALU work of the previous one.  Same arithmetic, bit-identical results.
+            for (int tile = group; tile < num_tiles; tile += ngroups) {
+                const int b = tile / tiles_per_img, t = tile % tiles_per_img;
+                const int g0 = (isA ? (t / tiles_j) * kTileM + (int)cx.rank * C::kM : (t % tiles_j) * NT + (int)cx.rank * C::kBRows) + wrow;
+                const float4* pb = params + (size_t)b * N;
+                const int cnt = sun_count(b), nchunks = sun_chunks(cnt), last = max(cnt, 1) - 1;
+                if (g0 >= R) {
+                    // rows beyond the image feed accumulator rows / columns that are never stored: nothing to write
+                    for (int c = 0; c < nchunks; ++c, ++it) {
+                        const int s = it % C::kStages;
+                        cx.producer_acquire(s, (it / C::kStages) & 1);
+                        cx.producer_commit(s);
+                    }
+                    continue;
+                }
+                const uint32_t tab = (isA ? cx.sX_u : cx.sY_u) + (uint32_t)g0 * 4u;
+                float xr[kSteps];
+#pragma unroll
+                for (int st = 0; st < kSteps; ++st) xr[st] = tc::lds_f32(tab + 4u * lane_row(st));
+                float4 pr[4];
+                auto load_params = [&](int c) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) pr[e] = __ldg(pb + min(c * C::kKC + 4 * ch + e, last));
+                };
+                tc::f32x2 nc2[2], k22[2], la2[2], vp[kSteps][2];
+                auto decode = [&](int c) {                   // pr (raw footprints of stage c) -> packed exponent coefficients
+                    float ctr[4], nk2[4], la[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const bool have = c * C::kKC + 4 * ch + e < cnt;
+                        ctr[e] = isA ? pr[e].x : pr[e].y;
+                        nk2[e] = -pr[e].z;
+                        la[e] = have ? (isA ? lg2_ftz(pr[e].w) : 0.f) + 14.f : -INFINITY;     // amplitude and the 2^14 scale; K padding: exact zeros
+                    }
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        nc2[h] = tc::pack2(-ctr[2 * h], -ctr[2 * h + 1]);
+                        k22[h] = tc::pack2(nk2[2 * h], nk2[2 * h + 1]);
+                        la2[h] = tc::pack2(la[2 * h], la[2 * h + 1]);
+                    }
+                };
+                auto eval = [&](int st) {
+                    const tc::f32x2 x2 = tc::pack2(xr[st], xr[st]);
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const tc::f32x2 d2 = tc::add2(x2, nc2[h]);
+                        float a0, a1;
+                        tc::unpack2(tc::fma2(tc::mul2(d2, k22[h]), d2, la2[h]), a0, a1);
+                        vp[st][h] = tc::pack2(ex2(a0), ex2(a1));
+                    }
+                };
+                auto store = [&](uint32_t base, int st) {
+                    uint32_t p1a, p1b, p2a, p2b;
+                    tc::split_f16x2_packed(vp[st][0].r, p1a, p2a);
+                    tc::split_f16x2_packed(vp[st][1].r, p1b, p2b);
+                    const uint32_t row = lane_row(st), sw = row & 7u;
+                    const uint32_t rb = base + (row >> 3) * 1024u + sw * 128u + 8u * ((uint32_t)ch & 1u);
+                    tc::sts_v2_b32(rb + ((((uint32_t)ch >> 1) ^ sw) << 4), p1a, p1b);
+                    tc::sts_v2_b32(rb + (((4u + ((uint32_t)ch >> 1)) ^ sw) << 4), p2a, p2b);
+                };
+                load_params(0);
+                decode(0);
+                if (nchunks > 1) load_params(1);
+#pragma unroll
+                for (int st = 0; st < kSteps; ++st) eval(st);
+#pragma unroll 1
+                for (int c = 0; c < nchunks; ++c, ++it) {
+                    const int s = it % C::kStages;
+                    const bool more = c + 1 < nchunks;
+                    if (more) {
+                        decode(c + 1);
+                        if (c + 2 < nchunks) load_params(c + 2);      // lands under this stage's work
+                    }
+                    {
+                        TC_STAT_BEGIN;
+                        cx.producer_acquire(s, (it / C::kStages) & 1);
+                        TC_STAT_END(2);
+                    }
+                    const uint32_t base = cx.smem_u + (uint32_t)(s * C::kStageBytes) + region;
+                    if (more) {
+#pragma unroll
+                        for (int st = 0; st < kSteps; ++st) {
+                            store(base, st);
+                            eval(st);
+                        }
+                    } else {
+#pragma unroll
+                        for (int st = 0; st < kSteps; ++st) store(base, st);
+                    }
+                    {
+                        TC_STAT_BEGIN;
+                        cx.producer_commit(s);
+                        TC_STAT_END(1);
+                    }
+                }
+            }
+        } else {
         int pending = -1;                            // stage whose stores are issued but not yet handed to the MMA warp
         static_assert(HELIO_FWD_DEFER == 1, "the forward producers are written for the deferred hand-off (measured: -5.7 %)");
         for (int tile = group; tile < num_tiles; tile += ngroups) {
@@ -428,10 +586,10 @@ splat_fwd_tc_kernel(const float4* __restrict__ params, const int* __restrict__ c
             // operand rows beyond the image only feed accumulator rows / columns that are never stored: skip the
             // Gaussians and leave the stage bytes as they are (accumulator rows and columns are independent)
             const bool dead = g0 >= R;
-            const uint32_t tab = (isA ? cx.sX_u : cx.sY_u) + (uint32_t)(g0 + rs) * 4u;
+            const uint32_t tab = (isA ? cx.sX_u : cx.sY_u) + (uint32_t)g0 * 4u;
             float xr[kSteps];
 #pragma unroll
-            for (int st = 0; st < kSteps; ++st) xr[st] = tc::lds_f32(tab + 4u * kRS * st);
+            for (int st = 0; st < kSteps; ++st) xr[st] = tc::lds_f32(tab + 4u * lane_row(st));
             const float4* pb = params + (size_t)b * N;
             const int cnt = sun_count(b), nchunks = sun_chunks(cnt), last = max(cnt, 1) - 1;
             // This lane's 4 heliostats of a stage arrive as raw float4 (index clamped so the load never needs a select),
@@ -442,19 +600,26 @@ splat_fwd_tc_kernel(const float4* __restrict__ params, const int* __restrict__ c
             // two buffers (even / odd stages) -- see the note at its definition for why that is not the default.
             float4 prA[4], prB[4];
             auto load_params = [&](float4 (&pr)[4], int c) {
+                if (HELIO_FWD_FULL_STAGE && (c + 1) * C::kKC <= cnt) {
+                    const float4* q = pb + (c * C::kKC + 4 * ch);
 #pragma unroll
-                for (int e = 0; e < 4; ++e) pr[e] = __ldg(pb + min(c * C::kKC + 4 * ch + e, last));
+                    for (int e = 0; e < 4; ++e) pr[e] = __ldg(q + e);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) pr[e] = __ldg(pb + min(c * C::kKC + 4 * ch + e, last));
+                }
             };
-            auto stage = [&](float4 (&pr)[4], const int c) {
+            auto stage = [&](float4 (&pr)[4], const int c, auto full_tag) {
                 float ctr[4], nk2[4], la[4];
+                constexpr bool full = decltype(full_tag)::value;       // all 32 heliostats of the stage exist
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    const bool have = c * C::kKC + 4 * ch + e < cnt;
+                    const bool have = full || c * C::kKC + 4 * ch + e < cnt;
                     ctr[e] = isA ? pr[e].x : pr[e].y;
                     nk2[e] = -pr[e].z;
                     // amplitude folded into the exponent (amp ~ 1: lg2.approx is exact to 2^-22 absolute there);
                     // K padding: 2^-inf = exact zeros
-                    la[e] = have ? (isA ? __log2f(pr[e].w) : 0.f) + (PREC == 1 ? 14.f : 0.f) : -INFINITY;   // f16x3: operands x 2^14
+                    la[e] = have ? (isA ? lg2_ftz(pr[e].w) : 0.f) + (PREC == 1 ? 14.f : 0.f) : -INFINITY;   // f16x3: operands x 2^14
                 }
 #if !HELIO_FWD_PREFETCH2
                 load_params(pr, c + 1 < nchunks ? c + 1 : c);      // A/B: the old one-stage-ahead prefetch (same buffer)
@@ -463,8 +628,9 @@ splat_fwd_tc_kernel(const float4* __restrict__ params, const int* __restrict__ c
                 // Hand the PREVIOUS stage over only after this stage's Gaussians have been evaluated: its shared-memory
                 // stores drain under the arithmetic.
                 float v[kSteps][4];
+                [[maybe_unused]] tc::f32x2 vp[kSteps][2];
                 if (!dead) {
-#if HELIO_PACKED2
+                    if constexpr (HELIO_PACKED2 || (HELIO_FWD_F16_TRUNC && PREC == 1)) {
                     // FADD2 / FMUL2 / FFMA2: the same IEEE operations, two heliostats per instruction
                     tc::f32x2 nc2[2], k22[2], la2[2];
 #pragma unroll
@@ -484,9 +650,10 @@ splat_fwd_tc_kernel(const float4* __restrict__ params, const int* __restrict__ c
                             tc::unpack2(a2, a0, a1);
                             v[st][2 * h] = ex2(a0);
                             v[st][2 * h + 1] = ex2(a1);
+                            if constexpr (PREC == 1) vp[st][h] = tc::pack2(v[st][2 * h], v[st][2 * h + 1]);
                         }
                     }
-#else
+                    } else {
 #pragma unroll
                     for (int st = 0; st < kSteps; ++st)
 #pragma unroll
@@ -494,7 +661,7 @@ splat_fwd_tc_kernel(const float4* __restrict__ params, const int* __restrict__ c
                             const float d = xr[st] - ctr[e];
                             v[st][e] = ex2(fmaf(d * nk2[e], d, la[e]));
                         }
-#endif
+                    }
                 }
                 {
                     TC_STAT_BEGIN;
@@ -516,12 +683,18 @@ splat_fwd_tc_kernel(const float4* __restrict__ params, const int* __restrict__ c
                     if (!dead) {
 #pragma unroll
                         for (int st = 0; st < kSteps; ++st) {
+#if HELIO_FWD_F16_TRUNC
+                            uint32_t p1a, p1b, p2a, p2b;
+                            tc::split_f16x2_packed(vp[st][0].r, p1a, p2a);
+                            tc::split_f16x2_packed(vp[st][1].r, p1b, p2b);
+#else
                             const uint32_t p1a = tc::f2h2(v[st][0], v[st][1]), p1b = tc::f2h2(v[st][2], v[st][3]);
                             float f0, f1, f2, f3;
                             tc::h22f(p1a, f0, f1);
                             tc::h22f(p1b, f2, f3);
                             const uint32_t p2a = tc::f2h2(v[st][0] - f0, v[st][1] - f1), p2b = tc::f2h2(v[st][2] - f2, v[st][3] - f3);
-                            const uint32_t row = (uint32_t)(kRS * st + rs), sw = row & 7u;
+#endif
+                            const uint32_t row = lane_row(st), sw = row & 7u;
                             const uint32_t rb = base + (row >> 3) * 1024u + sw * 128u + 8u * ((uint32_t)ch & 1u);
                             tc::sts_v2_b32(rb + ((((uint32_t)ch >> 1) ^ sw) << 4), p1a, p1b);
                             tc::sts_v2_b32(rb + (((4u + ((uint32_t)ch >> 1)) ^ sw) << 4), p2a, p2b);
@@ -557,19 +730,25 @@ splat_fwd_tc_kernel(const float4* __restrict__ params, const int* __restrict__ c
             if (nchunks > 1) load_params(prB, 1);
 #pragma unroll 1
             for (int c = 0; c < nchunks; c += 2) {
-                stage(prA, c);
-                if (c + 1 < nchunks) stage(prB, c + 1);
+                stage(prA, c, std::false_type{});
+                if (c + 1 < nchunks) stage(prB, c + 1, std::false_type{});
             }
 #else
             load_params(prA, 0);
 #pragma unroll 1
-            for (int c = 0; c < nchunks; ++c) stage(prA, c);
+            for (int c = 0; c < nchunks; ++c) {
+                if (HELIO_FWD_FULL_STAGE && (c + 1) * C::kKC <= cnt) stage(prA, c, std::true_type{});
+                else stage(prA, c, std::false_type{});
+            }
 #endif
         }
 #if HELIO_FWD_DEFER
         if (pending >= 0) cx.producer_commit(pending);
 #endif
+        }
         TC_STAT_FLUSH;
+        };
+        if (warp < C::kAWarps) produce(std::true_type{}); else produce(std::false_type{});
     } else if (warp == C::kMmaWarp) {
         // ================= MMA issuer (leader CTA of the group) =================
         if (cx.rank == 0) {
@@ -610,7 +789,7 @@ splat_fwd_tc_kernel(const float4* __restrict__ params, const int* __restrict__ c
             if constexpr (FUSE == kFuseLoss) tinv_t = fmaxf(__ldg(fz.tx + b), 1e-6f);
             {
                 TC_STAT_BEGIN;
-                tc::mbar_wait_sleep(&cx.tfull[acc], (tcount >> 1) & 1);
+                tc::mbar_wait_sleep<HELIO_EPI_SLEEP_FWD_NS>(&cx.tfull[acc], (tcount >> 1) & 1);
                 TC_STAT_END(1);
             }
             tc::tc_fence_after();
@@ -941,7 +1120,7 @@ splat_bwd_tc_kernel(const float4* __restrict__ params, const int* __restrict__ c
 #pragma unroll 1
             for (int prod = 0; prod < 2; ++prod) {
                 const float ctr = prod == 0 ? p.y : p.x;
-                const float la = dead + (prod == 0 ? 0.f : log2f(p.w)) + (PREC == 1 ? 14.f : 0.f);   // amplitude (and the f16x3 scale 2^14) folded into the exponent
+                const float la = dead + (prod == 0 ? 0.f : lg2_ftz(p.w)) + (PREC == 1 ? 14.f : 0.f);   // amplitude (and the f16x3 scale 2^14) folded into the exponent
                 const uint32_t tab = (prod == 0 ? cx.sY_u : cx.sX_u) + (uint32_t)q0 * (PREC == 1 ? 32u : 16u);
 #pragma unroll 1
                 for (int pbk = 0; pbk < pblocks; ++pbk) {
@@ -1074,25 +1253,44 @@ splat_bwd_tc_kernel(const float4* __restrict__ params, const int* __restrict__ c
                         const int s = it % C::kStages;
                         const int k0 = c * C::kKC;
                         float4 vals[8];
-                        const int row0 = gw * 32 + (lane >> 3), ch = lane & 7;     // product 0: 8 lanes per 128-byte row segment
+                        // product 0: 8 lanes per 128-byte row segment, a warp instruction covers 4 rows.  HELIO_BWD_STAGER_ROWMAP = 1 makes
+                        // them rows {0, 1, 4, 5} / {2, 3, 6, 7} of an 8-row swizzle atom, which removes the 2-way bank conflict of the
+                        // 8-byte f16x3 stores (as in the forward producers) -- measured on B200: K3 +3 % SLOWER at R = 256, +1.6 % at
+                        // R = 64, -1.6 % at R = 128, so the consecutive rows stay.
+                        const int ch = lane & 7, rl = lane >> 3;
+#if HELIO_BWD_STAGER_ROWMAP
+                        const int row_l = gw * 32 + (rl & 1) + 4 * (rl >> 1);
+                        auto qrow = [](int q) { return 8 * (q >> 1) + 2 * (q & 1); };
+#else
+                        const int row_l = gw * 32 + rl;
+                        auto qrow = [](int q) { return 4 * q; };
+#endif
+                        auto srow = [&](int q) { return row_l + qrow(q); };
                         const int j = pbk * NT + row_base + t;                     // product 1: this thread's image column
                         // 32 K values (kb .. kb + 31) of this thread's share of the operand tile -> vals[8]
                         //   product 0: operand row = image row i (accumulator column), K = image column j: 8 lanes cover one
-                        //              128-byte row segment, a warp instruction covers 4 rows; vals[q] = row (row0 + 4 q), K kb + 4 ch .. + 3
+                        //              128-byte row segment, a warp instruction covers 4 rows; vals[q] = row srow(q), K kb + 4 ch .. + 3
                         //   product 1: operand row = image column j, K = image row i: lanes read consecutive columns of one
                         //              image row (coalesced), transposing in registers; vals[q] = K kb + 4 q .. + 3 of row t
                         auto load32 = [&](const int kb) {
                             // whole operand tile inside the image: no per-element bounds checks (the common case)
                             const bool inside = vec && kb + 32 <= R && pbk * NT + row_base + C::kBRows <= R;
                             if (prod == 0) {
-                                if (inside) {
-                                    const float4* src = reinterpret_cast<const float4*>(gb + (size_t)(pbk * NT + row_base + row0) * R + kb) + ch;
+                                if (inside && R == NT) {
+                                    // R = 64 / 128 / 256 exactly (the usual resolutions): the row stride is a compile-time constant and
+                                    // the loads of a stage share one address register with immediate offsets
+                                    const float4* src = reinterpret_cast<const float4*>(gb + (size_t)(row_base + row_l) * NT + kb) + ch;
 #pragma unroll
-                                    for (int q = 0; q < 8; ++q) vals[q] = __ldg(src + (size_t)q * R);   // 4 rows = R float4
+                                    for (int q = 0; q < 8; ++q) vals[q] = __ldg(src + qrow(q) * (NT / 4));
+                                } else if (inside) {
+                                    const float4* src = reinterpret_cast<const float4*>(gb + (size_t)(pbk * NT + row_base + row_l) * R + kb) + ch;
+                                    const size_t R4 = (size_t)(R >> 2);                                 // one image row in float4
+#pragma unroll
+                                    for (int q = 0; q < 8; ++q) vals[q] = __ldg(src + (size_t)qrow(q) * R4);
                                 } else {
 #pragma unroll
                                     for (int q = 0; q < 8; ++q) {
-                                        const int i = pbk * NT + row_base + row0 + q * 4, jj = kb + ch * 4;
+                                        const int i = pbk * NT + row_base + srow(q), jj = kb + ch * 4;
                                         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                                         if (i < R) {
                                             const float* src = gb + (size_t)i * R + jj;
@@ -1109,7 +1307,16 @@ splat_bwd_tc_kernel(const float4* __restrict__ params, const int* __restrict__ c
                                     }
                                 }
                             } else {
-                                if (inside) {
+                                if (inside && R == NT) {
+                                    const float* src = gb + (size_t)kb * NT + j;
+#pragma unroll
+                                    for (int q = 0; q < 8; ++q) {
+                                        vals[q].x = __ldg(src + (4 * q) * NT);
+                                        vals[q].y = __ldg(src + (4 * q + 1) * NT);
+                                        vals[q].z = __ldg(src + (4 * q + 2) * NT);
+                                        vals[q].w = __ldg(src + (4 * q + 3) * NT);
+                                    }
+                                } else if (inside) {
                                     const float* src = gb + (size_t)kb * R + j;
 #pragma unroll
                                     for (int q = 0; q < 8; ++q) {
@@ -1157,7 +1364,7 @@ splat_bwd_tc_kernel(const float4* __restrict__ params, const int* __restrict__ c
                                         tc::split_f16x2(vals[q].x * gs, vals[q].y * gs, p1a, p2a);
                                         tc::split_f16x2(vals[q].z * gs, vals[q].w * gs, p1b, p2b);
 #endif
-                                        const uint32_t row = (uint32_t)(row0 + q * 4), sw = row & 7u;
+                                        const uint32_t row = (uint32_t)srow(q), sw = row & 7u;
                                         const uint32_t off = (row >> 3) * 1024u + sw * 128u + ((((uint32_t)(4 * h) + ((uint32_t)ch >> 1)) ^ sw) << 4) + 8u * ((uint32_t)ch & 1u);
                                         tc::sts_v2_b32(hi_base + off, p1a, p1b);
                                         tc::sts_v2_b32(lo_base + off, p2a, p2b);
@@ -1195,7 +1402,7 @@ splat_bwd_tc_kernel(const float4* __restrict__ params, const int* __restrict__ c
                         uint32_t offs[8];
                         if (prod == 0) {
 #pragma unroll
-                            for (int q = 0; q < 8; ++q) offs[q] = tc::sw128_offset((uint32_t)(row0 + q * 4), (uint32_t)ch);
+                            for (int q = 0; q < 8; ++q) offs[q] = tc::sw128_offset((uint32_t)srow(q), (uint32_t)ch);
                         } else {
 #pragma unroll
                             for (int q = 0; q < 8; ++q) offs[q] = tc::sw128_offset((uint32_t)t, (uint32_t)q);
@@ -1306,7 +1513,7 @@ splat_bwd_tc_kernel(const float4* __restrict__ params, const int* __restrict__ c
                     const int acc = sub & 1;
                     {
                         TC_STAT_BEGIN;
-                        tc::mbar_wait_sleep(&cx.tfull[acc], (sub >> 1) & 1);
+                        tc::mbar_wait_sleep<HELIO_EPI_SLEEP_BWD_NS>(&cx.tfull[acc], (sub >> 1) & 1);
                         TC_STAT_END(1);
                     }
                     tc::tc_fence_after();

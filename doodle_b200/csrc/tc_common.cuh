@@ -67,6 +67,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 
 // generic-proxy smem writes -> visible to the async proxy (tcgen05.mma operand reads)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// the same for every state space (a CTA pair's leader orders its peer's shared memory too)
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async.shared::cluster;" ::: "memory"); }
 
 // ---- explicit shared-state-space accesses (32-bit shared addresses) --------------------------
 // The operand tiles are addressed through pointers the compiler cannot prove to be shared memory; generic
@@ -183,8 +185,9 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank)
         : "memory");
 }
 // long waits (epilogue waiting for a whole tile): back off so the spin does not eat issue slots
+template <int NS = 64>
 __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
-    while (!mbar_try_wait(bar, parity)) __nanosleep(64);
+    while (!mbar_try_wait(bar, parity)) __nanosleep(NS);
 }
 __device__ __forceinline__ void tmem_alloc_2cta(uint32_t* dst_smem, uint32_t ncols) {  // one warp in EACH CTA of the pair
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)

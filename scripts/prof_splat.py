@@ -36,4 +36,6 @@ if a.what == "fwd":
 else:
     lib.helio_splat_bwd(P(p), P(g), B, N, R, 15.0, 15.0, P(mom), a.impl, None)
 e1.record(); torch.cuda.synchronize()
-print(f"{a.what} impl {a.impl} B={B} N={N} R={R}: {e0.elapsed_time(e1):.3f} ms")
+out = img if a.what == "fwd" else mom
+digest = int(out.view(torch.int32).to(torch.int64).sum().item()) & 0xFFFFFFFFFFFF      # order-independent checksum of the result bits
+print(f"{a.what} impl {a.impl} B={B} N={N} R={R}: {e0.elapsed_time(e1):.3f} ms  bits {digest:012x}")
