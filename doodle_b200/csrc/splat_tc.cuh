@@ -84,7 +84,9 @@
 #define HELIO_CONSUMER_FENCE 0
 #endif
 #ifndef HELIO_BWD_STAGER_ROWMAP
-#define HELIO_BWD_STAGER_ROWMAP 0
+// 1: the K3 stagers of product 0 visit the rows of a swizzle atom in the bank-conflict-free order of the forward producers
+// (measured on B200: K3 -3.4 % at R = 64, -1.2 % at R = 128, unchanged at R = 256); 0: consecutive rows
+#define HELIO_BWD_STAGER_ROWMAP 1
 #endif
 #ifndef HELIO_EPI_SLEEP_FWD_NS
 // nanosleep between the epilogue warps' polls of the accumulator-full barrier.  The polls are 12-16 % of the warp instructions
@@ -462,12 +464,14 @@ splat_fwd_tc_kernel(const float4* __restrict__ params, const int* __restrict__ c
         const int rs = lane >> 3, ch = lane & 7;
         const uint32_t region = (isA ? 0u : (uint32_t)C::kBOff) + (uint32_t)(wrow >> 3) * 1024u;
         const uint32_t lo_delta = isA ? C::kABytes : C::kBBytes;
-        // rows visited by this lane: wrow + lane_row(step).  A step covers rows {0, 1, 4, 5} or {2, 3, 6, 7} of an 8-row swizzle
-        // atom: two rows whose first 64 bytes land in banks 0-15 and two in banks 16-31, so that the f16x3 stores (8 bytes per
-        // lane, one 64-byte half row per piece) touch every bank exactly twice -- consecutive rows {4 st .. 4 st + 3} put all
-        // four half rows on the same 16 banks (ncu: half of the kernel's shared-memory store wavefronts were conflicts).
+        // rows visited by this lane: wrow + lane_row(step).  A step covers rows {0, 4, 1, 5} or {2, 6, 3, 7} of an 8-row swizzle
+        // atom, in that order over the lane groups rs = 0..3.  The f16x3 stores are 8 bytes per lane (one 64-byte half row per
+        // piece and row) and the LSU handles a 64-bit warp store as two half-warps: each half (rs = 0, 1 / rs = 2, 3) then holds
+        // one row whose half lands in banks 0-15 (swizzle phase < 4) and one in banks 16-31, i.e. 128 bytes over 32 banks, one
+        // wavefront.  Consecutive rows {4 st .. 4 st + 3} put both half rows of a half-warp on the same 16 banks (ncu source
+        // page: 3.6 wavefronts per STS.64 instead of 2, half of the kernel's shared-memory store wavefronts).
         auto lane_row = [&](int st) -> uint32_t {
-            return 8u * (uint32_t)(st >> 1) + 2u * (uint32_t)(st & 1) + (uint32_t)(rs & 1) + 4u * (uint32_t)(rs >> 1);
+            return 8u * (uint32_t)(st >> 1) + 2u * (uint32_t)(st & 1) + 4u * (uint32_t)(rs & 1) + (uint32_t)(rs >> 1);
         };
         auto row_off = [&](int st) -> uint32_t {
             const uint32_t row = lane_row(st);
@@ -1253,13 +1257,12 @@ splat_bwd_tc_kernel(const float4* __restrict__ params, const int* __restrict__ c
                         const int s = it % C::kStages;
                         const int k0 = c * C::kKC;
                         float4 vals[8];
-                        // product 0: 8 lanes per 128-byte row segment, a warp instruction covers 4 rows.  HELIO_BWD_STAGER_ROWMAP = 1 makes
-                        // them rows {0, 1, 4, 5} / {2, 3, 6, 7} of an 8-row swizzle atom, which removes the 2-way bank conflict of the
-                        // 8-byte f16x3 stores (as in the forward producers) -- measured on B200: K3 +3 % SLOWER at R = 256, +1.6 % at
-                        // R = 64, -1.6 % at R = 128, so the consecutive rows stay.
+                        // product 0: 8 lanes per 128-byte row segment, a warp instruction covers 4 rows: rows {0, 4, 1, 5} / {2, 6, 3, 7}
+                        // of an 8-row swizzle atom, which keeps the 8-byte f16x3 stores free of bank conflicts (see the forward
+                        // producers), or consecutive rows with HELIO_BWD_STAGER_ROWMAP = 0
                         const int ch = lane & 7, rl = lane >> 3;
 #if HELIO_BWD_STAGER_ROWMAP
-                        const int row_l = gw * 32 + (rl & 1) + 4 * (rl >> 1);
+                        const int row_l = gw * 32 + 4 * (rl & 1) + (rl >> 1);
                         auto qrow = [](int q) { return 8 * (q >> 1) + 2 * (q & 1); };
 #else
                         const int row_l = gw * 32 + rl;
