@@ -76,7 +76,7 @@ HELIO_API int helio_set_tc_pair_mode(int mode);
  * the accuracy the tf32 hi/lo split keeps), three kind::f16 MMAs per K-step, fp32 accumulation, exact 2^-28 unscale in
  * the epilogue.  2 (default): auto = f16x3 (same measured accuracy as 3xTF32, half the tensor work: faster at every
  * shape); mode 0 keeps the 3xTF32 contraction BASELINE.json names selectable.
- * Process-wide; initial value from HELIO_FWD_PREC.  The backward (unbounded image gradient) always uses 3xTF32. */
+ * Process-wide; initial value from HELIO_FWD_PREC.  The backward has its own switch (helio_set_bwd_precision). */
 HELIO_API int helio_set_fwd_precision(int mode);
 
 /* Backward splat operand format inside helio_step_bwd.  0: 3xTF32.  1: "f16x3, K = 64" -- the Gaussian operand scaled by
