@@ -463,7 +463,7 @@ splat_fwd_tc_kernel(const float4* __restrict__ params, const int* __restrict__ c
         const int wrow = pw * kRows;                                     // first operand row of this warp (CTA-local)
         const int rs = lane >> 3, ch = lane & 7;
         const uint32_t region = (isA ? 0u : (uint32_t)C::kBOff) + (uint32_t)(wrow >> 3) * 1024u;
-        const uint32_t lo_delta = isA ? C::kABytes : C::kBBytes;
+        [[maybe_unused]] const uint32_t lo_delta = isA ? C::kABytes : C::kBBytes;
         // rows visited by this lane: wrow + lane_row(step).  A step covers rows {0, 4, 1, 5} or {2, 6, 3, 7} of an 8-row swizzle
         // atom, in that order over the lane groups rs = 0..3.  The f16x3 stores are 8 bytes per lane (one 64-byte half row per
         // piece and row) and the LSU handles a 64-bit warp store as two half-warps: each half (rs = 0, 1 / rs = 2, 3) then holds
@@ -602,7 +602,8 @@ splat_fwd_tc_kernel(const float4* __restrict__ params, const int* __restrict__ c
             // memory operation of the thread, i.e. for what is left of the L2 latency of that prefetch: 14 % of a producer
             // warp's time (scripts/tc_stats.py).  HELIO_FWD_PREFETCH2 = 1 moves the loads behind the fence, two stages ahead in
             // two buffers (even / odd stages) -- see the note at its definition for why that is not the default.
-            float4 prA[4], prB[4];
+            float4 prA[4];
+            [[maybe_unused]] float4 prB[4];
             auto load_params = [&](float4 (&pr)[4], int c) {
                 if (HELIO_FWD_FULL_STAGE && (c + 1) * C::kKC <= cnt) {
                     const float4* q = pb + (c * C::kKC + 4 * ch);
