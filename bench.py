@@ -59,6 +59,8 @@ def parse():
     ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling block (N > 1)")
     ap.add_argument("--no-both-3xtf32", action="store_true", help="skip the side measurement with both contractions in 3xTF32")
     ap.add_argument("--e2e-serial", action="store_true", help="e2e arm with caller-side copies instead of the host-action step")
+    ap.add_argument("--host-chunks", type=int, default=0, help="slices of the sun batch the host-action step overlaps its copies in (0 = the env's default)")
+    ap.add_argument("--e2e-only", action="store_true", help="tuning aid: print the e2e arm's ms per step and exit")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-culled", action="store_true", help="skip the opt-in footprint-culling side measurement")
     ap.add_argument("--no-small-field", action="store_true", help="skip the N=50, R=128, B=25 env-steps/s side measurement")
@@ -497,9 +499,17 @@ def main_ours(args):
         h_metrics.copy_(torch.stack([m["mse"], m["dist"], m["bound"], m["alignment_loss"]]).detach(), non_blocking=True)
         torch.cuda.current_stream().synchronize()      # the caller reads the result every step
 
+    if args.host_chunks > 0:
+        env.host_chunks = args.host_chunks
     for _ in range(2):
         e2e_step()
     ms_e2e = timed(e2e_step, steps) / steps
+    if args.e2e_only:
+        if rank == 0:
+            print(json.dumps(dict(e2e_ms_per_step=ms_e2e, host_chunks=env._host_chunks(B), device_ms_per_step=ms_step)))
+        if world > 1:
+            _leave_process_group(torch, dist, [ENV[0]])
+        return 0
 
     # ---- host link while every rank copies at once (explains the e2e scaling) ------------------------------------
     def link_gbs(dst, src, reps=5):

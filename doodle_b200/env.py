@@ -212,7 +212,8 @@ class HelioEnv(_EnvBase):
         self.check_finite = check_finite
         self.fused_step = fused_step
         self.cull = cull                               # footprint culling of the noisy render (helio_cull), off = dense
-        self.host_chunks = 4                           # backward slices when the action lives in host memory
+        self.host_chunks = "auto"                      # slices of the sun batch a host-resident action's step overlaps its copies in:
+                                                       # an int, or "auto" = 8 for batches of >= 24 waves of tiles, else 4 (measured)
         self._copy_stream = None
         self.distance_maps_impl = distance_maps_impl   # "auto"/"cuda": GPU EDT; "scipy": the reference's host path
         self._target_cache = None
@@ -377,6 +378,12 @@ class HelioEnv(_EnvBase):
                 assert not math.isinf(dist_l), "Distance loss is Inf"
                 assert not math.isinf(bound), "Boundary loss is Inf"
 
+    def _host_chunks(self, B: int) -> int:
+        if self.host_chunks != "auto":
+            return int(self.host_chunks)
+        from .functional import _wave_quantum
+        return 8 if B >= 24 * _wave_quantum(self.noisy_field.device) else 4
+
     def close(self):
         """Raise pending asserts and release the captured CUDA graphs (and the static buffers they own).  A sharded env
         whose graphs captured the NCCL all-reduce must be closed before ``torch.distributed.destroy_process_group()``:
@@ -477,7 +484,7 @@ class HelioEnv(_EnvBase):
             img, packed, _actual, refl, ideal_normals, bounds, angles, per_img, target, tx, action_dev = HostStepFn.apply(
                 act.contiguous(), self.sun_pos, _cf(nf._select_errors(B)), nf.heliostat_positions, self.distance_maps, nf.scene(),
                 nf._geom_workspace(B), R, nf.splat_impl, nf.splat_impl if nf.splat_impl_bwd is None else nf.splat_impl_bwd,
-                cached[0], cached[1], self._copy_stream, self.host_chunks, self.cull)
+                cached[0], cached[1], self._copy_stream, self._host_chunks(B), self.cull)
             if cached[0] is None:
                 self._store_target(target, tx)
             out = SimpleNamespace(refl=refl, bounds=bounds, angles=angles)

@@ -418,15 +418,26 @@ class StepFn(torch.autograd.Function):
         return (g_action,) + (None,) * 14
 
 
-def _host_slices(B: int, chunks: int, small_first: bool):
+def _host_slices(B: int, chunks: int, small_first: bool, quantum: int = 0):
     """[(b0, nb)] slices of the sun batch for overlapping host copies with kernels.  The one copy that cannot hide -- the first
-    host->device slice of the forward, the last device->host slice of the backward -- is a quarter of the others."""
+    host->device slice of the forward, the last device->host slice of the backward -- is a quarter of the others.
+    ``quantum`` (the SM count): slice sizes are rounded to whole waves of the persistent splat kernels (one sun = one tile of a
+    CTA or CTA pair at R <= 256), so that only one slice carries a ragged last wave -- as the unsliced launch does -- instead
+    of every slice (1260 suns on 74 CTA pairs = 17.03 waves: 18 are paid)."""
     chunks = max(1, min(int(chunks), B))
     if chunks == 1:
         return [(0, B)]
     small = max(1, int(round(0.25 * B / (chunks - 0.75))))
-    rest = B - small
-    sizes = [rest // (chunks - 1) + (1 if i < rest % (chunks - 1) else 0) for i in range(chunks - 1)]
+    q = int(quantum)
+    if q > 1 and B >= 2 * q * chunks:
+        small = max(q, small // q * q)
+        body = max(q, int(round((B - small) / (chunks - 1) / q)) * q)
+        while body > q and B - small - body * (chunks - 2) < q // 2:
+            body -= q
+        sizes = [body] * (chunks - 2) + [B - small - body * (chunks - 2)]      # the ragged remainder rides on one slice
+    else:
+        rest = B - small
+        sizes = [rest // (chunks - 1) + (1 if i < rest % (chunks - 1) else 0) for i in range(chunks - 1)]
     sizes = [small] + sizes if small_first else sizes + [small]
     out, b0 = [], 0
     for nb in sizes:
@@ -434,6 +445,18 @@ def _host_slices(B: int, chunks: int, small_first: bool):
             out.append((b0, nb))
             b0 += nb
     return out
+
+
+_SM_COUNT = {}
+
+
+def _wave_quantum(dev) -> int:
+    """SM count of the device (slice granularity of HostStepFn)."""
+    idx = torch.device(dev).index
+    idx = torch.cuda.current_device() if idx is None else idx
+    if idx not in _SM_COUNT:
+        _SM_COUNT[idx] = int(torch.cuda.get_device_properties(idx).multi_processor_count)
+    return _SM_COUNT[idx]
 
 
 class HostStepFn(torch.autograd.Function):
@@ -476,7 +499,7 @@ class HostStepFn(torch.autograd.Function):
         render_target = target is None
         # With the target to render the whole copy hides under it; with a cached target the forward itself runs in
         # slices of the sun batch, each starting when its slice of the action has landed.
-        fwd_slices = _host_slices(B, 1 if render_target else chunks, small_first=True)
+        fwd_slices = _host_slices(B, 1 if render_target else chunks, small_first=True, quantum=_wave_quantum(dev))
         fwd_chunks = len(fwd_slices)
         landed = []
         action_host3 = action_host.reshape(B, N, 3)
@@ -551,7 +574,7 @@ class HostStepFn(torch.autograd.Function):
         sl = lambda t, b0, nb: None if t is None else t.narrow(0, b0, nb)
         global _LAUNCHES
         with _Call("step_bwd_host", dev):
-            for b0, nb in _host_slices(B, chunks, small_first=False):
+            for b0, nb in _host_slices(B, chunks, small_first=False, quantum=_wave_quantum(g_action.device)):
                 refl_g = None if gs[4] is None else gs[4].view(B, N, 3).narrow(0, b0, nb)
                 rc = lib.helio_step_bwd(
                     C.byref(scene), _ptr(helio), _ptr(sl(sun, b0, nb)), _ptr(sl(action, b0, nb)), _ptr(sl(errs, b0, nb)),

@@ -176,3 +176,22 @@ def test_angular_action_space_matches_reference_rotation():
     np.testing.assert_allclose(gr.numpy(), g["grad"], rtol=1e-5, atol=1e-9)
     n3 = angles_to_normals(torch.as_tensor(g["angles"]).view(3, -1, 2), g["normals"].shape[1])    # [B,N,2] layout
     assert torch.equal(n3, n.detach())
+
+
+def test_host_slices_cover_the_batch_in_whole_waves():
+    """HostStepFn's slices of the sun batch: a partition of [0, B), the exposed slice (first of the forward, last of the backward)
+    a quarter of the others, and -- for batches of many waves -- every slice but one a multiple of the SM count."""
+    from doodle_b200.functional import _host_slices
+    for B in (1, 5, 25, 512, 1184, 2368, 4096, 16384):
+        for chunks in (1, 3, 4, 8):
+            for small_first in (True, False):
+                for q in (0, 148):
+                    sl = _host_slices(B, chunks, small_first, q)
+                    assert sl[0][0] == 0 and all(nb > 0 for _, nb in sl)
+                    assert all(sl[i][0] + sl[i][1] == sl[i + 1][0] for i in range(len(sl) - 1))
+                    assert sl[-1][0] + sl[-1][1] == B and len(sl) <= chunks
+                    if len(sl) > 1:
+                        small = sl[0][1] if small_first else sl[-1][1]
+                        assert small <= min(nb for _, nb in sl)
+                    if q and B >= 2 * q * chunks and chunks > 1:
+                        assert sum(1 for _, nb in sl if nb % q) <= 1, (B, chunks, sl)
