@@ -377,6 +377,41 @@ def gpu_eager_numbers(torch, dev, N, R, budget_s=20.0):
                      "evals/s of a chunk is the rate of the full workload (independent suns)")
 
 
+def _snapshot_step(torch, env, action0):
+    """(image, action gradient of mse + bound + alignment, action gradient of the full objective) of one env step on the bench
+    inputs.  The distance-weighted L1 term is left out of the first gradient: its image gradient is sign(diff) * dmap, a step
+    function of the image, so two forward passes that differ in the last bits flip it on pixels where |diff| is at rounding level
+    (the reference's own fp32 does, under any reordering) -- that measures the kink of |x|, not the contraction's accuracy."""
+    a = action0.detach().clone().requires_grad_(True)
+    obs, m, _ = env.step(a)
+    (m["mse"] + m["bound"] + m["alignment_loss"]).backward(retain_graph=True)
+    g_smooth = a.grad.detach().reshape(-1, 3).clone()
+    a.grad = None
+    (m["mse"] + m["dist"] + m["bound"] + m["alignment_loss"]).backward()
+    return obs["img"].detach().clone(), g_smooth, a.grad.detach().reshape(-1, 3).clone()
+
+
+def _compare_snapshots(torch, got, ref):
+    """How far the step in the default operand formats (f16x3) is from the same step in 3xTF32, in units of BASELINE.json's
+    tolerances: images 1e-4 relative + 1e-6 absolute; action gradients 1e-3 relative, elementwise as tests/conftest.py checks
+    them (1e-3 |ref| + 1e-3 median|ref| + 1e-5 of the heliostat's gradient norm).  < 1 = inside the tolerance."""
+    (img, g, gf), (img_r, g_r, gf_r) = got, ref
+    img_ratio = float(((img - img_r).abs() / (1e-6 + 1e-4 * img_r.abs())).max())
+    live = g_r.abs()[g_r.abs() > 1e-30]
+    med = float(live.median()) if live.numel() else 0.0
+    tol = 1e-3 * g_r.abs() + 1e-3 * med + 1e-5 * g_r.abs().amax(dim=1, keepdim=True)
+    g_ratio = float(((g - g_r).abs() / tol.clamp_min(1e-38)).max())
+    return dict(image_max_diff_over_tolerance=img_ratio, gradient_max_diff_over_tolerance=g_ratio,
+                image_max_rel_diff=float(((img - img_r).abs().max()) / img_r.abs().max().clamp_min(1e-30)),
+                gradient_max_norm_rel_diff=float((g - g_r).abs().max() / g_r.abs().max().clamp_min(1e-30)),
+                full_objective_gradient_max_norm_rel_diff=float((gf - gf_r).abs().max() / gf_r.abs().max().clamp_min(1e-30)),
+                note="same inputs, same cached target; tolerances of BASELINE.json (images rtol 1e-4 / atol 1e-6, gradients 1e-3 "
+                     "relative, elementwise); values < 1 are inside the tolerance.  The elementwise gradient figure is for mse + bound "
+                     "+ alignment; the distance-weighted L1 term's image gradient is sign(diff) * dmap, which flips on pixels whose "
+                     "|diff| is at rounding level whenever the forward changes in its last bits (in any fp32 implementation), so the "
+                     "full objective is reported in the max norm only")
+
+
 def _leave_process_group(torch, dist, envs):
     """Release captured graphs (a sharded small field's graphs hold NCCL kernels), then destroy the process group under a
     watchdog: a hung teardown must not cost GPU time."""
@@ -691,11 +726,19 @@ def main_ours(args):
                           note="helio_set_fwd_precision(0) + helio_set_bwd_precision(0): both contractions in 3xTF32, the format BASELINE.json "
                                "names (the defaults are the f16x3 formats: same 22-bit operand accuracy, half the tensor work); same "
                                "results within the parity tolerances")
+            snap_t = _snapshot_step(torch, ENV[0], action0)            # image + action gradient of one step in 3xTF32
         except Exception as e:
             tf32x3 = dict(error=repr(e))
+            snap_t = None
         finally:
             _lib.load().helio_set_bwd_precision(bwd_mode)
             _lib.load().helio_set_fwd_precision(2)
+        if snap_t is not None:
+            try:
+                tf32x3["default_formats_vs_3xtf32"] = _compare_snapshots(torch, _snapshot_step(torch, ENV[0], action0), snap_t)
+            except Exception as e:
+                tf32x3["default_formats_vs_3xtf32"] = dict(error=repr(e))
+            del snap_t
     small = None
     if world == 1 and not args.no_small_field:
         try:
