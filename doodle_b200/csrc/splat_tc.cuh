@@ -45,6 +45,9 @@
 // residual taken through an fp16 -> fp32 round trip (2^-23 v, 1.5 more instructions per Gaussian).
 #define HELIO_FWD_F16_TRUNC 1
 #endif
+#ifndef HELIO_FWD_DUO
+#define HELIO_FWD_DUO 1     // forward, images of at most 64 pixels a side: two images per 128 x 128 tile (0: one per 128 x 64 tile)
+#endif
 #ifndef HELIO_FWD_SWP
 #define HELIO_FWD_SWP 1     // f16x3 forward producers software-pipelined across stages (see the kernel)
 #endif
@@ -429,7 +432,11 @@ struct FwdFuse {
 template <int NT, int CG, int PS, int FUSE, int PREC, int STG>
 __global__ void __launch_bounds__(SplatFwdTc<NT, CG, PS, PREC, STG>::kThreads, 1)
 splat_fwd_tc_kernel(const float4* __restrict__ params, const int* __restrict__ counts, float* __restrict__ img, int N, int R,
-                    Axis ax, Axis ay, int tiles_i, int tiles_j, int num_tiles, FwdFuse fz) {
+                    Axis ax, Axis ay, int tiles_i, int tiles_j, int num_tiles, FwdFuse fz, int duo_B) {
+    // duo_B > 0 ("two images per tile", images of at most 64 pixels a side on the 128 x 128 single-CTA tile): tile t holds
+    // images 2 t and 2 t + 1 of duo_B, A = [Gx_2t ; Gx_2t+1], B = [Gy_2t ; Gy_2t+1] (64 rows each), and only the two diagonal
+    // 64 x 64 blocks of the accumulator are images.  The off-diagonal half of the MMA work is wasted, but at this size the
+    // kernel is bound by its producer warps, and a 128 x 64 tile would leave the two that own A rows 64..127 idle.
     using C = SplatFwdTc<NT, CG, PS, PREC, STG>;
     extern __shared__ uint8_t smem_raw[];
     SplatTcCtx<C, CG> cx;
@@ -441,6 +448,11 @@ splat_fwd_tc_kernel(const float4* __restrict__ params, const int* __restrict__ c
     auto sun_count = [&](int b) { return counts ? __ldg(counts + b) : N; };
     auto sun_chunks = [&](int cnt) { return max(1, (cnt + C::kKC - 1) / C::kKC); };
     const int tiles_per_img = tiles_i * tiles_j;
+    // stages of a tile: every role counts them alike (two-image tiles: the longer of the two culled lists)
+    auto tile_chunks = [&](int tile) {
+        if (duo_B > 0) return sun_chunks(max(sun_count(2 * tile), sun_count(min(2 * tile + 1, duo_B - 1))));
+        return sun_chunks(sun_count(tile / tiles_per_img));
+    };
     const int group = blockIdx.x / CG, ngroups = gridDim.x / CG;
     constexpr int kTileM = C::kM * CG;
 
@@ -487,11 +499,19 @@ splat_fwd_tc_kernel(const float4* __restrict__ params, const int* __restrict__ c
             // split and stored while step st of stage c + 1 is evaluated into the registers it frees, in one basic block, so
             // the MUFUs of one stage fill under the ALU work of the previous one.  Same arithmetic, bit-identical results.
             for (int tile = group; tile < num_tiles; tile += ngroups) {
-                const int b = tile / tiles_per_img, t = tile % tiles_per_img;
-                const int g0 = (isA ? (t / tiles_j) * kTileM + (int)cx.rank * C::kM : (t % tiles_j) * NT + (int)cx.rank * C::kBRows) + wrow;
+                int b = tile / tiles_per_img;
+                const int t = tile % tiles_per_img;
+                int g0 = (isA ? (t / tiles_j) * kTileM + (int)cx.rank * C::kM : (t % tiles_j) * NT + (int)cx.rank * C::kBRows) + wrow;
+                bool off_img = false;                // two-image tile, odd batch: the second image of the last tile does not exist
+                if (duo_B > 0) {
+                    b = 2 * tile + (wrow >> 6);
+                    off_img = b >= duo_B;
+                    b = min(b, duo_B - 1);
+                    g0 = wrow & 63;
+                }
                 const float4* pb = params + (size_t)b * N;
-                const int cnt = sun_count(b), nchunks = sun_chunks(cnt), last = max(cnt, 1) - 1;
-                if (g0 >= R) {
+                const int cnt = sun_count(b), nchunks = tile_chunks(tile), last = max(cnt, 1) - 1;
+                if (g0 >= R || off_img) {
                     // rows beyond the image feed accumulator rows / columns that are never stored: nothing to write
                     for (int c = 0; c < nchunks; ++c, ++it) {
                         const int s = it % C::kStages;
@@ -585,17 +605,25 @@ splat_fwd_tc_kernel(const float4* __restrict__ params, const int* __restrict__ c
         int pending = -1;                            // stage whose stores are issued but not yet handed to the MMA warp
         static_assert(HELIO_FWD_DEFER == 1, "the forward producers are written for the deferred hand-off (measured: -5.7 %)");
         for (int tile = group; tile < num_tiles; tile += ngroups) {
-            const int b = tile / tiles_per_img, t = tile % tiles_per_img;
-            const int g0 = (isA ? (t / tiles_j) * kTileM + (int)cx.rank * C::kM : (t % tiles_j) * NT + (int)cx.rank * C::kBRows) + wrow;
+            int b = tile / tiles_per_img;
+            const int t = tile % tiles_per_img;
+            int g0 = (isA ? (t / tiles_j) * kTileM + (int)cx.rank * C::kM : (t % tiles_j) * NT + (int)cx.rank * C::kBRows) + wrow;
+            bool off_img = false;
+            if (duo_B > 0) {
+                b = 2 * tile + (wrow >> 6);
+                off_img = b >= duo_B;
+                b = min(b, duo_B - 1);
+                g0 = wrow & 63;
+            }
             // operand rows beyond the image only feed accumulator rows / columns that are never stored: skip the
             // Gaussians and leave the stage bytes as they are (accumulator rows and columns are independent)
-            const bool dead = g0 >= R;
+            const bool dead = g0 >= R || off_img;
             const uint32_t tab = (isA ? cx.sX_u : cx.sY_u) + (uint32_t)g0 * 4u;
             float xr[kSteps];
 #pragma unroll
             for (int st = 0; st < kSteps; ++st) xr[st] = tc::lds_f32(tab + 4u * lane_row(st));
             const float4* pb = params + (size_t)b * N;
-            const int cnt = sun_count(b), nchunks = sun_chunks(cnt), last = max(cnt, 1) - 1;
+            const int cnt = sun_count(b), nchunks = tile_chunks(tile), last = max(cnt, 1) - 1;
             // This lane's 4 heliostats of a stage arrive as raw float4 (index clamped so the load never needs a select),
             // prefetched one stage ahead into the buffer the current stage has just decoded.  The hand-over's
             // fence.proxy.async compiles to MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC, and the MEMBAR waits for every outstanding
@@ -761,7 +789,7 @@ splat_fwd_tc_kernel(const float4* __restrict__ params, const int* __restrict__ c
             uint32_t it = 0, tcount = 0;
             for (int tile = group; tile < num_tiles; tile += ngroups, ++tcount) {
                 const int acc = tcount & 1;
-                const int nchunks = sun_chunks(sun_count(tile / tiles_per_img));
+                const int nchunks = tile_chunks(tile);
                 {
                     TC_STAT_BEGIN;
                     cx.mma_wait_tempty(acc, (tcount >> 1) & 1);
@@ -787,8 +815,18 @@ splat_fwd_tc_kernel(const float4* __restrict__ params, const int* __restrict__ c
         uint32_t tcount = 0;
         TC_STAT_DECL;
         for (int tile = group; tile < num_tiles; tile += ngroups, ++tcount) {
-            const int b = tile / tiles_per_img, t = tile % tiles_per_img;
-            const int i0 = (t / tiles_j) * kTileM + (int)cx.rank * C::kM, j0 = (t % tiles_j) * NT;
+            int b = tile / tiles_per_img;
+            const int t = tile % tiles_per_img;
+            int i0 = (t / tiles_j) * kTileM + (int)cx.rank * C::kM, j0 = (t % tiles_j) * NT;
+            // two-image tile: lane quarters 0, 1 hold image 2 t (accumulator columns 0..63), quarters 2, 3 image 2 t + 1 (64..127)
+            int qrow = q, coff = 0, ncols = NT;
+            bool img_ok = true;
+            if (duo_B > 0) {
+                b = 2 * tile + (q >> 1);
+                img_ok = b < duo_B;
+                b = min(b, duo_B - 1);
+                i0 = 0, j0 = 0, qrow = q & 1, coff = (q >> 1) * 64, ncols = 64;
+            }
             const int acc = tcount & 1;
             float tinv_t = 1.f;                      // kFuseLoss: the image's normaliser, fetched before the wait
             if constexpr (FUSE == kFuseLoss) tinv_t = fmaxf(__ldg(fz.tx + b), 1e-6f);
@@ -798,8 +836,8 @@ splat_fwd_tc_kernel(const float4* __restrict__ params, const int* __restrict__ c
                 TC_STAT_END(1);
             }
             tc::tc_fence_after();
-            const int i = i0 + q * 32 + lane;
-            const size_t row_off = ((size_t)b * R + i) * R + j0;
+            const int i = img_ok ? i0 + qrow * 32 + lane : R;      // a missing second image: every row is out of range
+            const size_t row_off = ((size_t)b * R + min(i, R - 1)) * R + j0;
             float* dst = img + row_off;
             // kFuseFeed: optional second copy of the image (e.g. the newest slot of a rollout's history buffer, batch stride given)
             float* dst2 = nullptr;
@@ -825,10 +863,11 @@ splat_fwd_tc_kernel(const float4* __restrict__ params, const int* __restrict__ c
                 }
             };
 #pragma unroll 1
-            for (int cb = 0; cb < NT; cb += 32) {
+            for (int cc = 0; cc < ncols; cc += 32) {
+                const int cb = cc;                                   // column offset inside the image tile
                 if (j0 + cb >= R) break;
                 float v[32];
-                tc::tmem_ld_32x32(taddr + cb, v);
+                tc::tmem_ld_32x32(taddr + coff + cc, v);
                 if constexpr (PREC == 1) {               // f16x3: both operands carried a factor 2^14
 #pragma unroll
                     for (int e = 0; e < 32; ++e) v[e] *= 3.7252902984619140625e-09f;   // 2^-28, exact
@@ -852,7 +891,7 @@ splat_fwd_tc_kernel(const float4* __restrict__ params, const int* __restrict__ c
                     if constexpr (FUSE == kFuseLoss) {           // all 16 loads in flight before the first use
 #pragma unroll
                         for (int k = 0; k < 8; ++k) {
-                            const int gi = i0 + q * 32 + 4 * k + rrow;
+                            const int gi = i0 + qrow * 32 + 4 * k + rrow;
                             const size_t o = ((size_t)b * R + min(gi, R - 1)) * R + gj;
                             tq[k] = __ldg(reinterpret_cast<const float4*>(fz.target + o));
                             dq[k] = __ldg(reinterpret_cast<const float4*>(fz.dmaps + o));
@@ -860,9 +899,9 @@ splat_fwd_tc_kernel(const float4* __restrict__ params, const int* __restrict__ c
                     }
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
-                        const int row = 4 * k + rrow, gi = i0 + q * 32 + row;
+                        const int row = 4 * k + rrow, gi = i0 + qrow * 32 + row;
                         const float4 x = tc::lds_v4_volatile(stg + (uint32_t)row * 128u + ((uint32_t)(ch ^ (row & 7)) << 4));
-                        if (gi < R) {
+                        if (gi < R && img_ok) {
                             *reinterpret_cast<float4*>(img + ((size_t)b * R + gi) * R + gj) = x;
                             if constexpr (FUSE == kFuseFeed)
                                 if (dst2) *reinterpret_cast<float4*>(dst2 + (size_t)gi * R + gj) = x;
@@ -910,7 +949,7 @@ splat_fwd_tc_kernel(const float4* __restrict__ params, const int* __restrict__ c
             cx.epilogue_release(acc);
             if constexpr (FUSE == kFuseMax) {
                 f0 = warp_max(f0);
-                if (lane == 0) atomicMax(reinterpret_cast<int*>(fz.tile_max + b), __float_as_int(f0));
+                if (lane == 0 && img_ok) atomicMax(reinterpret_cast<int*>(fz.tile_max + b), __float_as_int(f0));
             }
             if constexpr (FUSE == kFuseLoss || FUSE == kFuseFeed) {
                 f0 = warp_sum(f0), f1 = warp_sum(f1), f2 = warp_sum(f2);
@@ -966,15 +1005,17 @@ inline int splat_tc_fwd_partials_per_image(int R, int num_sms, int pair) {
 
 template <int NT, int CG, int PS, int PREC = 0, int STG = 0>
 inline cudaError_t launch_splat_fwd_tc(const float* params, const int* counts, float* img, int B, int N, int R, float width,
-                                       float height, int num_sms, cudaStream_t st, int fuse, const FwdFuse& fz) {
+                                       float height, int num_sms, cudaStream_t st, int fuse, const FwdFuse& fz, bool duo = false) {
     using C = SplatFwdTc<NT, CG, PS, PREC, STG>;
-    const int tiles_i = (R + C::kM * CG - 1) / (C::kM * CG), tiles_j = (R + NT - 1) / NT;
-    const long long num_tiles = (long long)B * tiles_i * tiles_j;
+    // duo: two images of at most 64 pixels a side per 128 x 128 tile (see the kernel); plain max / no epilogue fusion only
+    if (duo && !(NT == 128 && CG == 1 && PS == 1 && R <= 64 && (fuse == kFuseNone || fuse == kFuseMax))) return cudaErrorInvalidValue;
+    const int tiles_i = duo ? 1 : (R + C::kM * CG - 1) / (C::kM * CG), tiles_j = duo ? 1 : (R + NT - 1) / NT;
+    const long long num_tiles = duo ? ((long long)B + 1) / 2 : (long long)B * tiles_i * tiles_j;
     if (num_tiles > 0x7fffffffLL) return cudaErrorInvalidValue;
     auto go = [&](auto kernel) {
         return launch_tc_groups<CG>(kernel, num_tiles, num_sms, C::kThreads, C::kSmemBytes, st,
                                     reinterpret_cast<const float4*>(params), counts, img, N, R, make_axis(width, R),
-                                    make_axis(height, R), tiles_i, tiles_j, (int)num_tiles, fz);
+                                    make_axis(height, R), tiles_i, tiles_j, (int)num_tiles, fz, duo ? B : 0);
     };
     if (fuse == kFuseMax) return go(splat_fwd_tc_kernel<NT, CG, PS, kFuseMax, PREC, STG>);
     if constexpr (STG == 1) {                        // the loss / feed epilogues work on the staged (coalesced) layout
@@ -997,6 +1038,8 @@ inline cudaError_t splat_tc_fwd(const float* params, float* img, int B, int N, i
     // staged epilogue (see splat_fwd_tc_kernel): when the epilogue is a large share of a tile
     if (fuse == kFuseLoss || fuse == kFuseFeed) split = 1;      // those epilogues exist for the staged stores only
     const bool stg = fuse == kFuseLoss || fuse == kFuseFeed || (split != 2 && (prec == 1 || sun_avg_k(N) < 1024));
+    // images of at most 64 pixels a side: two per 128 x 128 tile (all eight producer warps live), see the kernel
+    const bool duo = HELIO_FWD_DUO && R <= 64 && B > 1 && split != 2 && (fuse == kFuseNone || fuse == kFuseMax);
     if (prec == 1) {                                 // opt-in f16x3 operands (see SplatFwdTc)
 #define HELIO_FWD16(NT_, CG_, PS_, STG_) launch_splat_fwd_tc<NT_, CG_, PS_, 1, STG_>(params, counts, img, B, N, R, width, height, num_sms, st, fuse, fz)
         if (R > 128) {
@@ -1004,12 +1047,15 @@ inline cudaError_t splat_tc_fwd(const float* params, float* img, int B, int N, i
             return stg ? HELIO_FWD16(256, 1, 1, 1) : HELIO_FWD16(256, 1, 1, 0);
         }
         if (R > 64) return split == 2 ? HELIO_FWD16(128, 1, 2, 0) : (stg ? HELIO_FWD16(128, 1, 1, 1) : HELIO_FWD16(128, 1, 1, 0));
+        if (duo) return stg ? launch_splat_fwd_tc<128, 1, 1, 1, 1>(params, counts, img, B, N, R, width, height, num_sms, st, fuse, fz, true)
+                            : launch_splat_fwd_tc<128, 1, 1, 1, 0>(params, counts, img, B, N, R, width, height, num_sms, st, fuse, fz, true);
         return stg ? HELIO_FWD16(64, 1, 1, 1) : HELIO_FWD16(64, 1, 1, 0);
 #undef HELIO_FWD16
     }
 #define HELIO_FWDS(NT_, CG_) launch_splat_fwd_tc<NT_, CG_, 1, 0, 1>(params, counts, img, B, N, R, width, height, num_sms, st, fuse, fz)
     if (stg) {
         if (R > 128) return splat_tc_fwd_cg(R, num_sms, pair) == 2 ? HELIO_FWDS(256, 2) : HELIO_FWDS(256, 1);
+        if (duo) return launch_splat_fwd_tc<128, 1, 1, 0, 1>(params, counts, img, B, N, R, width, height, num_sms, st, fuse, fz, true);
         return R > 64 ? HELIO_FWDS(128, 1) : HELIO_FWDS(64, 1);
     }
 #undef HELIO_FWDS
@@ -1020,6 +1066,7 @@ inline cudaError_t splat_tc_fwd(const float* params, float* img, int B, int N, i
     if (R > 64) return split == 2 ? HELIO_FWD(128, 1, 2) : HELIO_FWD(128, 1, 1);
     // measured on B200: twice the producer warps (split = 2) is 6-25 % slower at every shape, whether the extra warps
     // split the rows or the K range of a stage; kept as an A/B switch (HELIO_TC_FWD_SPLIT=2) only
+    if (duo) return launch_splat_fwd_tc<128, 1, 1, 0, 0>(params, counts, img, B, N, R, width, height, num_sms, st, fuse, fz, true);
     return split == 2 ? HELIO_FWD(64, 1, 2) : HELIO_FWD(64, 1, 1);
 #undef HELIO_FWD
 }
