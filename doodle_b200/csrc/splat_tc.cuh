@@ -67,16 +67,6 @@
 #define HELIO_BWD_DEFER 0
 #endif
 
-#ifndef HELIO_FWD_PREFETCH2
-// 1: forward producers keep the footprint parameters two stages ahead in two register buffers, the loads issued after the
-// proxy fence.  Measured on B200 (scripts/gpu_ab_fwd.sh): the fence wait drops from 14 % to 8 % of a producer warp's time,
-// but the second buffer needs 16 more registers, the kernel hits the 128-register ceiling of a 13-warp CTA (four warps
-// share one scheduler's 16 K registers), ptxas spills, and the forward gets SLOWER (3.51 -> 4.5 ms).  Kept as an A/B switch.
-#define HELIO_FWD_PREFETCH2 0
-#endif
-#ifndef HELIO_RELAXED_ARRIVE
-#define HELIO_RELAXED_ARRIVE 0   // 1: producers signal "stage written" with mbarrier.arrive.relaxed (see tc_common.cuh)
-#endif
 #ifndef HELIO_CONSUMER_FENCE
 // Where the generic -> async proxy fence between the producers' st.shared and the tensor core's operand reads sits.
 // 0: in every producer thread before its warp's arrive (the CUTLASS pattern).  fence.proxy.async compiles to MEMBAR.ALL.CTA +
@@ -285,13 +275,8 @@ struct SplatTcCtx {
 #endif
         __syncwarp();
         if ((threadIdx.x & 31) == 0) {
-#if HELIO_RELAXED_ARRIVE
-            if constexpr (CG == 2) tc::mbar_arrive_remote_relaxed(&full[s], 0);
-            else tc::mbar_arrive_relaxed(&full[s]);
-#else
             if constexpr (CG == 2) tc::mbar_arrive_remote(&full[s], 0);
             else tc::mbar_arrive(&full[s]);
-#endif
         }
     }
     // producer warp: wait until the MMAs that read stage s have retired
@@ -628,10 +613,10 @@ splat_fwd_tc_kernel(const float4* __restrict__ params, const int* __restrict__ c
             // prefetched one stage ahead into the buffer the current stage has just decoded.  The hand-over's
             // fence.proxy.async compiles to MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC, and the MEMBAR waits for every outstanding
             // memory operation of the thread, i.e. for what is left of the L2 latency of that prefetch: 14 % of a producer
-            // warp's time (scripts/tc_stats.py).  HELIO_FWD_PREFETCH2 = 1 moves the loads behind the fence, two stages ahead in
-            // two buffers (even / odd stages) -- see the note at its definition for why that is not the default.
+            // warp's time (scripts/tc_stats.py).  Moving the loads behind the fence, two stages ahead in two register buffers, was
+            // measured: the wait drops to 8 %, but 16 more registers hit the 128-register ceiling of a 13-warp CTA (four warps
+            // share one scheduler's 16 K registers), ptxas spills, and the forward gets slower (3.51 -> 4.5 ms).
             float4 prA[4];
-            [[maybe_unused]] float4 prB[4];
             auto load_params = [&](float4 (&pr)[4], int c) {
                 if (HELIO_FWD_FULL_STAGE && (c + 1) * C::kKC <= cnt) {
                     const float4* q = pb + (c * C::kKC + 4 * ch);
@@ -654,9 +639,7 @@ splat_fwd_tc_kernel(const float4* __restrict__ params, const int* __restrict__ c
                     // K padding: 2^-inf = exact zeros
                     la[e] = have ? (isA ? lg2_ftz(pr[e].w) : 0.f) + (PREC == 1 ? 14.f : 0.f) : -INFINITY;   // f16x3: operands x 2^14
                 }
-#if !HELIO_FWD_PREFETCH2
-                load_params(pr, c + 1 < nchunks ? c + 1 : c);      // A/B: the old one-stage-ahead prefetch (same buffer)
-#endif
+                load_params(pr, c + 1 < nchunks ? c + 1 : c);      // next stage's footprints, into the buffer just decoded
                 const int s = it % C::kStages;
                 // Hand the PREVIOUS stage over only after this stage's Gaussians have been evaluated: its shared-memory
                 // stores drain under the arithmetic.
@@ -701,9 +684,6 @@ splat_fwd_tc_kernel(const float4* __restrict__ params, const int* __restrict__ c
                     if (pending >= 0) cx.producer_commit(pending);
                     TC_STAT_END(1);
                 }
-#if HELIO_FWD_PREFETCH2
-                if (c + 2 < nchunks) load_params(pr, c + 2);       // this buffer's next stage; lands under two stages of work
-#endif
                 {
                     TC_STAT_BEGIN;
                     cx.producer_acquire(s, (it / C::kStages) & 1);
@@ -758,22 +738,12 @@ splat_fwd_tc_kernel(const float4* __restrict__ params, const int* __restrict__ c
                 pending = s;
                 ++it;
             };
-#if HELIO_FWD_PREFETCH2
-            load_params(prA, 0);
-            if (nchunks > 1) load_params(prB, 1);
-#pragma unroll 1
-            for (int c = 0; c < nchunks; c += 2) {
-                stage(prA, c, std::false_type{});
-                if (c + 1 < nchunks) stage(prB, c + 1, std::false_type{});
-            }
-#else
             load_params(prA, 0);
 #pragma unroll 1
             for (int c = 0; c < nchunks; ++c) {
                 if (HELIO_FWD_FULL_STAGE && (c + 1) * C::kKC <= cnt) stage(prA, c, std::true_type{});
                 else stage(prA, c, std::false_type{});
             }
-#endif
         }
 #if HELIO_FWD_DEFER
         if (pending >= 0) cx.producer_commit(pending);

@@ -17,15 +17,8 @@ __device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// Arrive WITHOUT release semantics, for the producers' "stage written" signal.  The default (.release.cta) makes the
-// compiler put a MEMBAR.ALL.CTA in front, which waits for every outstanding memory operation of the thread -- including
-// the parameter prefetch loads issued a few hundred cycles earlier (L2 latency), 14 % of a producer warp's time.  What the
-// consumer needs is already ordered explicitly: the operand bytes are shared-memory stores made visible to the async
-// proxy by fence.proxy.async, which this thread executes (and completes) before the arrive in program order; nothing the
-// MMA thread reads comes from global memory.
-__device__ __forceinline__ void mbar_arrive_relaxed(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
+// (An arrive WITHOUT release semantics, mbarrier.arrive.relaxed, was tried for the producers' "stage written" signal: the
+// MEMBAR.ALL.CTA in front of it stays -- it belongs to fence.proxy.async, not to the release -- so it bought nothing.)
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
@@ -168,14 +161,6 @@ __device__ __forceinline__ void cluster_sync() {
 // arrive on the mbarrier at the same shared-memory offset in CTA `rank` of the cluster.  Default semantics
 // (release at CTA scope): the data this guards is shared memory consumed by the async proxy, made visible by
 // fence.proxy.async before the arrive; a cluster-scope release would add MEMBAR.GPU + an L1 invalidate per call.
-__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint64_t* bar, uint32_t rank) {
-    asm volatile(
-        "{\n\t.reg .b32 ra;\n\t"
-        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-        "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t}"
-        ::"r"(smem_u32(bar)), "r"(rank)
-        : "memory");
-}
 __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
     asm volatile(
         "{\n\t.reg .b32 ra;\n\t"
